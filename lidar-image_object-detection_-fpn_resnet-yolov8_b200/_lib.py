@@ -1,0 +1,83 @@
+"""ctypes binding of libsfa_b200.so (include/sfa_b200.h).  There is NO CPU fallback: if the CUDA
+library cannot be loaded every entry point of this package raises."""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsfa_b200.so")
+
+c_float_p = ctypes.POINTER(ctypes.c_float)
+c_void_p = ctypes.c_void_p
+i32, i64, f32, sz = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
+
+
+class SfaBevParams(ctypes.Structure):
+    """struct SfaBevParams of include/sfa_b200.h."""
+    _fields_ = [("min_x", f32), ("max_x", f32), ("min_y", f32), ("max_y", f32), ("min_z", f32), ("max_z", f32),
+                ("discretization", f32), ("y_offset", f32), ("max_height", f32),
+                ("height", i32), ("width", i32), ("apply_filter", i32)]
+
+
+class SfaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libsfa_b200: %s (status %d)" % (msg, code))
+        self.code = code
+
+
+# every symbol include/sfa_b200.h declares: name -> (restype, argtypes)
+PROTOTYPES = {
+    "sfa_version": (ctypes.c_int, []),
+    "sfa_last_error": (ctypes.c_char_p, []),
+    "sfa_bev_workspace_bytes": (sz, [i32, ctypes.POINTER(SfaBevParams)]),
+    "sfa_bev_workspace_init": (ctypes.c_int, [c_void_p, sz, c_void_p]),
+    "sfa_bev_rasterize": (ctypes.c_int, [c_void_p, c_void_p, i32, i64, ctypes.POINTER(SfaBevParams), c_void_p,
+                                         c_void_p, c_void_p, c_void_p, sz, c_void_p]),
+    "sfa_filter_workspace_bytes": (sz, [i64]),
+    "sfa_filter_lidar": (ctypes.c_int, [c_void_p, i64, ctypes.POINTER(SfaBevParams), c_void_p, c_void_p, c_void_p,
+                                        sz, c_void_p]),
+    "sfa_nms": (ctypes.c_int, [c_void_p, i32, i32, i32, c_void_p, c_void_p]),
+    "sfa_topk": (ctypes.c_int, [c_void_p, i32, i32, i32, i32, i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p]),
+    "sfa_decode": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, i32, i32, i32, i32, i32, c_void_p,
+                                  c_void_p, c_void_p]),
+    "sfa_post_process": (ctypes.c_int, [c_void_p, i32, i32, i32, f32, f32, f32, f32, f32, f32, c_void_p, c_void_p,
+                                        c_void_p, c_void_p]),
+    "sfa_pipeline_create": (c_void_p, [i32, i32, i64, ctypes.POINTER(SfaBevParams), c_void_p, i32, i32, i32, i32]),
+    "sfa_pipeline_destroy": (None, [c_void_p]),
+    "sfa_pipeline_bev_host": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, i32, c_void_p, c_void_p]),
+    "sfa_pipeline_decode_host": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, i32,
+                                                c_void_p]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load():
+    """Returns the loaded library; raises (loudly) when it is missing — run build.py first."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    "libsfa_b200.so is not built (%s). Run `python __graft_entry__.py build`; this package has no "
+                    "CPU fallback." % LIB_PATH)
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in PROTOTYPES.items():
+                fn = getattr(lib, name)  # AttributeError if the .so is stale
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise SfaError(rc, (load().sfa_last_error() or b"").decode("utf-8", "replace"))
+
+
+def last_error():
+    return (load().sfa_last_error() or b"").decode("utf-8", "replace")

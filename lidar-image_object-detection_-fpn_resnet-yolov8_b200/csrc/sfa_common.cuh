@@ -1,0 +1,58 @@
+// Shared helpers for libsfa_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "sfa_b200.h"
+
+namespace sfa {
+
+// thread-local last-error message (sfa_last_error)
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define SFA_CUDA_TRY(expr)                                         \
+    do {                                                           \
+        cudaError_t _e = (expr);                                   \
+        if (_e != cudaSuccess) return ::sfa::cuda_fail(_e, #expr); \
+    } while (0)
+
+#define SFA_REQUIRE(cond, ...)                 \
+    do {                                       \
+        if (!(cond)) {                         \
+            ::sfa::set_error(__VA_ARGS__);     \
+            return SFA_ERR_INVALID_ARGUMENT;   \
+        }                                      \
+    } while (0)
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// ---- streaming memory access (data a CTA touches exactly once: keep it out of L1) ----
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream_f4(float4* p, const float4& v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+// ---- order-preserving float -> uint32 maps -------------------------------------------------------
+// Total order of the float VALUES (-0.0 == +0.0); `nan_key` is where NaN goes.
+__device__ __forceinline__ uint32_t orderable_u32(float f, uint32_t nan_key) {
+    uint32_t b = __float_as_uint(f);
+    if (b == 0x80000000u) b = 0u;  // -0.0 compares equal to +0.0
+    uint32_t k = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    return (f != f) ? nan_key : k;
+}
+__device__ __forceinline__ float orderable_to_float(uint32_t k) {
+    uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+    return __uint_as_float(b);
+}
+
+}  // namespace sfa

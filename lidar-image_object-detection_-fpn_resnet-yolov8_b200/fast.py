@@ -1,0 +1,190 @@
+"""Batched, device-resident API over libsfa_b200.so — the fast path a B200 inference loop uses.
+
+    rast = BevRasterizer(geometry.from_config(kitti_config), max_batch=64)
+    bev  = rast(points, offsets, max_points)        # cuda f32 [B,3,608,608]   (stage A)
+    det  = decode(hm, off, dir, z, dim, K=50)       # utils.evaluation_utils   (stage B)
+    rows, cls, keep = post_process_dense(det)
+
+PyTorch is used for device memory and streams only; all arithmetic happens in the CUDA library.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .geometry import BevGeometry
+
+
+def _require_cuda(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise TypeError("%s must be a CUDA tensor" % name)
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class BevRasterizer:
+    """Stage A for batches of sweeps resident in HBM (replaces get_filtered_lidar + makeBEVMap,
+    data_process/kitti_data_utils.py:228-241 and data_process/kitti_bev_utils.py:22-55)."""
+
+    def __init__(self, geom: BevGeometry, max_batch: int = 64, device=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("BevRasterizer needs a CUDA device (there is no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.geom = geom
+        self.max_batch = int(max_batch)
+        nbytes = self.lib.sfa_bev_workspace_bytes(self.max_batch, ctypes.byref(geom.params))
+        if nbytes == 0:
+            raise _lib.SfaError(-1, _lib.last_error() or "bad geometry")
+        with torch.cuda.device(self.device):
+            self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            off = (-self.workspace.data_ptr()) % 256
+            self._ws_ptr = self.workspace.data_ptr() + off
+            self._ws_bytes = nbytes
+            self.lut = torch.from_numpy(geom.lut32.copy()).to(self.device)
+            self.status = torch.zeros(2, dtype=torch.int32, device=self.device)
+            _lib.check(self.lib.sfa_bev_workspace_init(ctypes.c_void_p(self._ws_ptr), self._ws_bytes,
+                                                       _stream_ptr(self.device)))
+
+    def __call__(self, points, offsets, max_points, out=None):
+        """points [total,4] f32 cuda, offsets [B+1] i64 cuda, max_points: python int upper bound on
+        the points of any sweep.  Returns out [B,3,H,W] f32 (channel 0 intensity, 1 height, 2 density)."""
+        _require_cuda(points, "points")
+        _require_cuda(offsets, "offsets")
+        if points.dtype != torch.float32 or offsets.dtype != torch.int64:
+            raise TypeError("points must be float32 and offsets int64")
+        if not points.is_contiguous() or not offsets.is_contiguous():
+            raise ValueError("points / offsets must be contiguous")
+        B = offsets.numel() - 1
+        g = self.geom
+        if out is None:
+            out = torch.empty((B, 3, g.height, g.width), dtype=torch.float32, device=self.device)
+        elif out.shape != (B, 3, g.height, g.width) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError("out must be contiguous float32 [B,3,H,W]")
+        _lib.check(self.lib.sfa_bev_rasterize(_ptr(points), _ptr(offsets), B, int(max_points),
+                                              ctypes.byref(g.params), _ptr(self.lut), _ptr(out), _ptr(self.status),
+                                              ctypes.c_void_p(self._ws_ptr), self._ws_bytes, _stream_ptr(self.device)))
+        return out
+
+    def rasterize_uniform(self, points, out=None):
+        """points [B,N,4]: every sweep has N points."""
+        B, N = points.shape[0], points.shape[1]
+        offsets = torch.arange(B + 1, dtype=torch.int64, device=points.device) * N
+        return self(points.reshape(-1, 4), offsets, N, out=out)
+
+    def out_of_map_points(self, reset=True):
+        """Points seen since the last reset whose cell index fell outside the (H+1)x(W+1) map (the
+        reference raises IndexError for those).  Synchronises."""
+        n = int(self.status[0].item())
+        if reset:
+            self.status.zero_()
+        return n
+
+
+def filter_lidar_device(points, geom: BevGeometry):
+    """get_filtered_lidar (data_process/kitti_data_utils.py:228-241) on a CUDA [N,4] sweep:
+    returns the filtered, z-shifted sweep as a new CUDA tensor (one host sync to size it)."""
+    lib = _lib.load()
+    _require_cuda(points, "points")
+    points = points.contiguous()
+    n = points.shape[0]
+    out = torch.empty_like(points)
+    count = torch.zeros(1, dtype=torch.int64, device=points.device)
+    ws_bytes = lib.sfa_filter_workspace_bytes(n)
+    ws = torch.empty(max(ws_bytes, 4), dtype=torch.uint8, device=points.device)
+    _lib.check(lib.sfa_filter_lidar(_ptr(points), n, ctypes.byref(geom.params), _ptr(out), _ptr(count), _ptr(ws),
+                                    ws_bytes, _stream_ptr(points.device)))
+    return out[: int(count.item())]
+
+
+def post_process_dense(detections, num_classes=3, down_ratio=4, peak_thresh=0.2, cnf=None):
+    """Dense post_processing (utils/evaluation_utils.py:112-163) on CUDA detections [B,K,10]:
+    returns (rows [B,K,8] f32, cls [B,K] i32, keep [B,K] bool), all on the device."""
+    from .config import kitti_config
+    cnf = kitti_config if cnf is None else cnf
+    lib = _lib.load()
+    _require_cuda(detections, "detections")
+    det = detections.contiguous().float()
+    B, K = det.shape[0], det.shape[1]
+    rows = torch.empty((B, K, 8), dtype=torch.float32, device=det.device)
+    cls = torch.empty((B, K), dtype=torch.int32, device=det.device)
+    keep = torch.empty((B, K), dtype=torch.uint8, device=det.device)
+    _lib.check(lib.sfa_post_process(_ptr(det), B, K, int(num_classes), float(down_ratio), float(cnf.bound_size_y),
+                                    float(cnf.BEV_WIDTH), float(cnf.bound_size_x), float(cnf.BEV_HEIGHT),
+                                    float(peak_thresh), _ptr(rows), _ptr(cls), _ptr(keep), _stream_ptr(det.device)))
+    return rows, cls, keep.bool()
+
+
+class HostPipeline:
+    """Host-buffer entry points (sfa_pipeline_*): numpy / CPU tensors in, numpy out, with chunked,
+    overlapped H2D -> kernels -> D2H inside the library.  This is what the drop-in makeBEVMap /
+    decode wrappers and bench.py's `e2e` leg call."""
+
+    def __init__(self, geom: BevGeometry, max_frames=64, max_points=131072, C=3, h=152, w=152, K=50, device=0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("HostPipeline needs a CUDA device (there is no CPU fallback)")
+        self.geom, self.max_frames, self.max_points = geom, int(max_frames), int(max_points)
+        self.C, self.h, self.w, self.K = C, h, w, K
+        lut = np.ascontiguousarray(geom.lut32)
+        self._h = self.lib.sfa_pipeline_create(int(device), self.max_frames, self.max_points, ctypes.byref(geom.params),
+                                               lut.ctypes.data_as(ctypes.c_void_p), C, h, w, K)
+        if not self._h:
+            raise _lib.SfaError(-3, _lib.last_error())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.sfa_pipeline_destroy(ctypes.c_void_p(self._h))
+            self._h = None
+
+    __del__ = close
+
+    def bev(self, points, offsets, out=None):
+        """points [total,4] f32 (numpy or CPU tensor, ideally pinned), offsets [B+1] i64 -> [B,3,H,W] f32
+        numpy (or writes into `out`).  Returns (out, n_out_of_map)."""
+        pts = _as_host(points, np.float32)
+        offs = _as_host(offsets, np.int64)
+        B = offs.shape[0] - 1
+        g = self.geom
+        if out is None:
+            out = np.empty((B, 3, g.height, g.width), dtype=np.float32)
+        o = _as_host(out, np.float32)
+        status = np.zeros(2, dtype=np.uint32)
+        _lib.check(self.lib.sfa_pipeline_bev_host(ctypes.c_void_p(self._h), pts.ctypes.data_as(ctypes.c_void_p),
+                                                  offs.ctypes.data_as(ctypes.c_void_p), B,
+                                                  o.ctypes.data_as(ctypes.c_void_p),
+                                                  status.ctypes.data_as(ctypes.c_void_p)))
+        return out, int(status[0])
+
+    def decode(self, hm, cen_offset, direction, z_coor, dim, out=None):
+        """CPU heads [B,c,h,w] f32 -> detections [B,K,10] f32 numpy."""
+        hm_, dir_, z_, dim_ = (_as_host(t, np.float32) for t in (hm, direction, z_coor, dim))
+        off_ = _as_host(cen_offset, np.float32) if cen_offset is not None else None
+        B = hm_.shape[0]
+        if hm_.shape[1:] != (self.C, self.h, self.w):
+            raise ValueError("pipeline was created for heads %s, got %s" % ((self.C, self.h, self.w), hm_.shape[1:]))
+        if out is None:
+            out = np.empty((B, self.K, 10), dtype=np.float32)
+        o = _as_host(out, np.float32)
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p) if a is not None else ctypes.c_void_p(0)
+        _lib.check(self.lib.sfa_pipeline_decode_host(ctypes.c_void_p(self._h), vp(hm_), vp(off_), vp(dir_), vp(z_),
+                                                     vp(dim_), B, vp(o)))
+        return out
+
+
+def _as_host(a, dtype):
+    if isinstance(a, torch.Tensor):
+        if a.is_cuda:
+            raise TypeError("expected a host tensor")
+        a = a.detach().numpy()
+    a = np.asarray(a)
+    if a.dtype != dtype or not a.flags["C_CONTIGUOUS"]:
+        a = np.ascontiguousarray(a, dtype=dtype)
+    return a

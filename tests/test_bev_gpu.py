@@ -1,0 +1,186 @@
+"""GPU parity of stage A (sweep filter + BEV rasterisation) against the CPU oracle, through the
+C ABI (ctypes).  Integer quantities (occupied cells, winning point per cell, counts) and therefore
+all three float planes must be BIT-EXACT (the float maps are produced by the same fp32 operations;
+contract tolerance 1e-6 relative is asserted as well, and is met with zero error)."""
+import numpy as np
+import pytest
+import torch
+
+import sfa_oracle as O
+from conftest import pkg
+
+pytestmark = pytest.mark.gpu
+
+KINDS = ["uniform", "outside", "zties", "gridaligned", "bounds", "nonfinite", "onecell", "clustered"]
+
+
+def _geom(ogeom, apply_filter=True):
+    class Cnf:
+        BEV_HEIGHT, BEV_WIDTH, DISCRETIZATION = ogeom.BEV_HEIGHT, ogeom.BEV_WIDTH, ogeom.DISCRETIZATION
+    return pkg("geometry").BevGeometry(ogeom.boundary, Cnf, apply_filter=apply_filter)
+
+
+def _run_batch(cuda_device, sweeps, ogeom, apply_filter=True, max_batch=None):
+    fast = pkg("fast")
+    rast = fast.BevRasterizer(_geom(ogeom, apply_filter), max_batch=max_batch or max(1, len(sweeps)), device=cuda_device)
+    lens = [s.shape[0] for s in sweeps]
+    offsets = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int64, device=cuda_device)
+    allpts = np.concatenate(sweeps, 0) if sum(lens) else np.zeros((0, 4), np.float32)
+    pts = torch.from_numpy(allpts).to(cuda_device)
+    if pts.numel() == 0:
+        pts = torch.zeros((1, 4), dtype=torch.float32, device=cuda_device)[:0]
+    out = rast(pts, offsets, max(lens) if lens else 0)
+    torch.cuda.synchronize()
+    return out.cpu().numpy(), rast
+
+
+def _assert_bit_exact(got, want, what):
+    assert got.dtype == np.float32 and want.dtype == np.float32
+    if not np.array_equal(got.view(np.uint32), want.view(np.uint32)):
+        bad = np.argwhere(got.view(np.uint32) != want.view(np.uint32))
+        raise AssertionError("%s: %d cells differ, first at %s: got %r want %r" %
+                             (what, len(bad), bad[0], got[tuple(bad[0])], want[tuple(bad[0])]))
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=0)  # the contract's tolerance, trivially met
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("n", [0, 1, 5000, 120000])
+def test_bev_single_sweep_bit_exact(cuda_device, kind, n):
+    n = min(n, 100000) if kind == "onecell" else n
+    sweep = O.synth_sweep(17, n, O.KITTI, kind) if n else np.zeros((0, 4), np.float32)
+    got, rast = _run_batch(cuda_device, [sweep], O.KITTI)
+    want = O.make_bev_scatter(sweep, O.KITTI, True, np.float32)
+    _assert_bit_exact(got[0], want, "%s n=%d" % (kind, n))
+    assert rast.out_of_map_points() == 0
+
+
+def test_bev_matches_lexsort_formulation(cuda_device):
+    """Against the oracle's literal lexsort+unique port (float64 map cast to float32)."""
+    sweep = O.synth_sweep(3, 120000, O.KITTI, "zties")
+    got, _ = _run_batch(cuda_device, [sweep], O.KITTI)
+    ref = O.makeBEVMap(O.get_filtered_lidar(sweep.copy(), O.KITTI.boundary), O.KITTI.boundary, O.KITTI)
+    _assert_bit_exact(got[0], ref.astype(np.float32), "lexsort port")
+
+
+def test_bev_batch64_ragged_and_ring_reuse(cuda_device):
+    """BASELINE config[1] shape: 64 sweeps; ragged sizes; the scratch ring is reused 8 times, and the
+    same rasteriser is called twice (the workspace must come back clean)."""
+    rng = np.random.default_rng(5)
+    sweeps = []
+    for i in range(64):
+        n = int(rng.integers(0, 130000)) if i % 7 else 120000
+        sweeps.append(O.synth_sweep(100 + i, n, O.KITTI, KINDS[i % len(KINDS)] if n <= 100000 else "uniform")
+                      if n else np.zeros((0, 4), np.float32))
+    for attempt in range(2):
+        got, rast = _run_batch(cuda_device, sweeps, O.KITTI)
+        for i, s in enumerate(sweeps):
+            _assert_bit_exact(got[i], O.make_bev_scatter(s, O.KITTI, True, np.float32), "frame %d" % i)
+
+
+def test_bev_second_call_same_workspace(cuda_device):
+    fast = pkg("fast")
+    rast = fast.BevRasterizer(_geom(O.KITTI), max_batch=4, device=cuda_device)
+    for seed in (1, 2, 3):
+        sweeps = [O.synth_sweep(seed * 10 + j, 50000 + 1000 * j, O.KITTI, "zties") for j in range(11)]
+        lens = [s.shape[0] for s in sweeps]
+        offsets = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int64, device=cuda_device)
+        pts = torch.from_numpy(np.concatenate(sweeps, 0)).to(cuda_device)
+        got = rast(pts, offsets, max(lens)).cpu().numpy()
+        for i, s in enumerate(sweeps):
+            _assert_bit_exact(got[i], O.make_bev_scatter(s, O.KITTI, True, np.float32), "seed %d frame %d" % (seed, i))
+
+
+def test_bev_back_boundary_negative_row_wrap(cuda_device):
+    """boundary_back (config/kitti_config.py:36-43): x in [-50, 0] -> negative rows wrap (numpy
+    negative indexing) — rows 1..607 occupied, row 0 only from x == 0."""
+    sweep = O.synth_sweep(8, 80000, O.KITTI_BACK, "uniform")
+    got, _ = _run_batch(cuda_device, [sweep], O.KITTI_BACK)
+    _assert_bit_exact(got[0], O.make_bev_scatter(sweep, O.KITTI_BACK, True, np.float32), "back")
+
+
+@pytest.mark.parametrize("kind", ["uniform", "zties", "outside"])
+def test_bev_argoverse_range_250k(cuda_device, kind):
+    """BASELINE config[3]: Argoverse-range sweeps (~250k points, +-50 m, z in [-3, 5])."""
+    sweep = O.synth_sweep(21, 250000, O.ARGOVERSE, kind)
+    got, _ = _run_batch(cuda_device, [sweep], O.ARGOVERSE)
+    _assert_bit_exact(got[0], O.make_bev_scatter(sweep, O.ARGOVERSE, True, np.float32), "argoverse " + kind)
+
+
+def test_bev_without_filter_negative_z_and_nan_z(cuda_device):
+    """makeBEVMap alone (apply_filter=0): z not shifted, may be negative; NaN z sorts last."""
+    sweep = O.synth_sweep(9, 60000, O.KITTI, "zties")
+    sweep[::97, 2] = np.nan
+    got, _ = _run_batch(cuda_device, [sweep], O.KITTI, apply_filter=False)
+    want = O.make_bev_scatter(sweep, O.KITTI, apply_filter=False, dtype=np.float32)
+    assert np.array_equal(got[0], want, equal_nan=True)
+    assert np.array_equal(np.isnan(got[0]), np.isnan(want))
+
+
+def test_bev_odd_grid_scalar_finalize(cuda_device):
+    """H*W not a multiple of 4 takes the scalar finalize path."""
+    g = O.Geometry(boundary={"minX": 0, "maxX": 30, "minY": -15, "maxY": 15, "minZ": -2, "maxZ": 2},
+                   BEV_HEIGHT=301, BEV_WIDTH=301)
+    sweep = O.synth_sweep(4, 40000, g, "zties")
+    got, _ = _run_batch(cuda_device, [sweep], g)
+    _assert_bit_exact(got[0], O.make_bev_scatter(sweep, g, True, np.float32), "301x301")
+
+
+def test_bev_out_of_map_is_counted_not_written(cuda_device):
+    """Unfiltered points beyond the map make the reference raise IndexError; the kernel skips and
+    counts them, and the drop-in wrapper turns the count into IndexError."""
+    sweep = O.synth_sweep(2, 1000, O.KITTI, "uniform")
+    sweep[:10, 0] = 500.0  # row 6080
+    got, rast = _run_batch(cuda_device, [sweep], O.KITTI, apply_filter=False)
+    assert rast.out_of_map_points() == 10
+    want = O.make_bev_scatter(sweep[10:], O.KITTI, apply_filter=False, dtype=np.float32)
+    # indices shift by 10 but winners are the same points
+    _assert_bit_exact(got[0], want, "skip out-of-map")
+    with pytest.raises(IndexError):
+        pkg("data_process.kitti_bev_utils").makeBEVMap(sweep, O.KITTI.boundary)
+
+
+def test_bev_full_size_properties(cuda_device):
+    """Size-independent properties at BASELINE's full batch (64 x 120k): (1) permutation invariance
+    of everything but tie order is covered elsewhere; here: density plane decodes to counts whose sum
+    equals the number of kept, un-cropped points; occupied cells agree across the three planes;
+    re-running is idempotent (bitwise identical output)."""
+    sweeps = [O.synth_sweep(1000 + i, 120000, O.KITTI, "uniform") for i in range(64)]
+    got1, rast = _run_batch(cuda_device, sweeps, O.KITTI)
+    got2, _ = _run_batch(cuda_device, sweeps, O.KITTI)
+    assert np.array_equal(got1.view(np.uint32), got2.view(np.uint32))
+    lut = O.density_lut64().astype(np.float32)
+    for i in (0, 31, 63):
+        counts = np.searchsorted(lut, got1[i, 2])
+        assert counts.max() < 63
+        rows, cols, win, cnt, _ = O.bev_cell_selection(sweeps[i], O.KITTI, True)
+        assert counts.sum() == cnt.sum()
+        assert np.array_equal(got1[i, 2] > 0, counts > 0)
+        # intensity is exactly the winner's 4th column
+        assert np.array_equal(got1[i, 0][rows, cols], sweeps[i][win, 3])
+
+
+def test_host_pipeline_and_dropin_makeBEVMap(cuda_device):
+    """Host-buffer C ABI (sfa_pipeline_bev_host) and the reference-signature wrappers:
+    makeBEVMap returns the reference's float64 map bit for bit."""
+    bevmod = pkg("data_process.kitti_bev_utils")
+    datmod = pkg("data_process.kitti_data_utils")
+    sweep = O.synth_sweep(12, 120000, O.KITTI, "outside")
+    filt = datmod.get_filtered_lidar(sweep, O.KITTI.boundary)
+    want_f = O.get_filtered_lidar(sweep.copy(), O.KITTI.boundary)
+    assert filt.dtype == np.float32 and np.array_equal(filt.view(np.uint32), want_f.view(np.uint32))
+    m = bevmod.makeBEVMap(filt, O.KITTI.boundary)
+    want = O.makeBEVMap(want_f, O.KITTI.boundary, O.KITTI)
+    assert m.dtype == np.float64 and m.shape == (3, 608, 608)
+    assert np.array_equal(m.view(np.uint64), want.view(np.uint64))
+    fused = bevmod.makeBEVMap_from_raw(sweep, O.KITTI.boundary)
+    _assert_bit_exact(fused, want.astype(np.float32), "fused raw")
+    # batched host pipeline, ragged, more frames than one chunk
+    fast = pkg("fast")
+    pl = fast.HostPipeline(_geom(O.KITTI), max_frames=20, max_points=130000, C=0, h=1, w=1, K=1)
+    sweeps = [O.synth_sweep(40 + i, 100000 + 1000 * i, O.KITTI, "zties") for i in range(20)]
+    lens = [s.shape[0] for s in sweeps]
+    out, bad = pl.bev(np.concatenate(sweeps), np.concatenate([[0], np.cumsum(lens)]).astype(np.int64))
+    assert bad == 0
+    for i, s in enumerate(sweeps):
+        _assert_bit_exact(out[i], O.make_bev_scatter(s, O.KITTI, True, np.float32), "host frame %d" % i)
+    pl.close()
