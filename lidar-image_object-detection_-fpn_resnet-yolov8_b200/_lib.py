@@ -19,6 +19,11 @@ class SfaBevParams(ctypes.Structure):
                 ("height", i32), ("width", i32), ("apply_filter", i32)]
 
 
+class SfaKernelStat(ctypes.Structure):
+    """struct SfaKernelStat of include/sfa_b200.h."""
+    _fields_ = [("name", ctypes.c_char * 40), ("launches", ctypes.c_uint64), ("total_ms", ctypes.c_double)]
+
+
 class SfaError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("libsfa_b200: %s (status %d)" % (msg, code))
@@ -29,6 +34,9 @@ class SfaError(RuntimeError):
 PROTOTYPES = {
     "sfa_version": (ctypes.c_int, []),
     "sfa_last_error": (ctypes.c_char_p, []),
+    "sfa_kernel_launches": (ctypes.c_uint64, []),
+    "sfa_profile_begin": (ctypes.c_int, []),
+    "sfa_profile_end": (ctypes.c_int, [ctypes.POINTER(SfaKernelStat), i32]),
     "sfa_bev_workspace_bytes": (sz, [i32, ctypes.POINTER(SfaBevParams)]),
     "sfa_bev_workspace_init": (ctypes.c_int, [c_void_p, sz, c_void_p]),
     "sfa_bev_rasterize": (ctypes.c_int, [c_void_p, c_void_p, i32, i64, ctypes.POINTER(SfaBevParams), c_void_p,
@@ -81,3 +89,26 @@ def check(rc):
 
 def last_error():
     return (load().sfa_last_error() or b"").decode("utf-8", "replace")
+
+
+def kernel_launches():
+    """Kernels libsfa_b200.so has launched in this process so far."""
+    return int(load().sfa_kernel_launches())
+
+
+class profile:
+    """with _lib.profile() as p: ...   ->   p.stats = {kernel name: (launches, total_ms)} (device time
+    from CUDA events the library records around each of its launches)."""
+
+    def __enter__(self):
+        check(load().sfa_profile_begin())
+        self.stats = {}
+        return self
+
+    def __exit__(self, *exc):
+        buf = (SfaKernelStat * 32)()
+        n = load().sfa_profile_end(buf, 32)
+        if n < 0:
+            check(n)
+        self.stats = {buf[i].name.decode(): (int(buf[i].launches), float(buf[i].total_ms)) for i in range(n)}
+        return False

@@ -11,6 +11,9 @@
 
 #include <string.h>
 #include <stdlib.h>
+#include <atomic>
+#include <mutex>
+#include <string>
 #include <vector>
 
 namespace sfa {
@@ -29,12 +32,71 @@ int cuda_fail(cudaError_t e, const char* what) {
     return SFA_ERR_CUDA;
 }
 
+// ---- launch accounting and per-kernel event timing ------------------------------------------
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<bool> g_profiling{false};
+static std::mutex g_prof_mutex;
+struct ProfSpan { std::string name; cudaEvent_t a = nullptr, b = nullptr; };
+static std::vector<ProfSpan> g_spans;
+
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool profiling_on() { return g_profiling.load(std::memory_order_relaxed); }
+
+void profile_mark(const char* name, cudaStream_t stream, bool begin) {
+    std::lock_guard<std::mutex> lk(g_prof_mutex);
+    if (begin) {
+        ProfSpan s;
+        s.name = name;
+        if (cudaEventCreate(&s.a) != cudaSuccess || cudaEventCreate(&s.b) != cudaSuccess) return;
+        cudaEventRecord(s.a, stream);
+        g_spans.push_back(s);
+    } else if (!g_spans.empty()) {
+        cudaEventRecord(g_spans.back().b, stream);
+    }
+}
+
 }  // namespace sfa
 
 using namespace sfa;
 
 extern "C" int sfa_version(void) { return SFA_B200_VERSION; }
 extern "C" const char* sfa_last_error(void) { return g_error; }
+extern "C" uint64_t sfa_kernel_launches(void) { return g_launches.load(); }
+
+extern "C" int sfa_profile_begin(void) {
+    std::lock_guard<std::mutex> lk(g_prof_mutex);
+    for (ProfSpan& s : g_spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    g_spans.clear();
+    g_profiling.store(true);
+    return SFA_OK;
+}
+
+extern "C" int sfa_profile_end(SfaKernelStat* stats, int32_t max_stats) {
+    g_profiling.store(false);
+    std::lock_guard<std::mutex> lk(g_prof_mutex);
+    int n = 0;
+    int rc = SFA_OK;
+    for (ProfSpan& s : g_spans) {
+        float ms = 0.f;
+        cudaError_t e = cudaEventSynchronize(s.b);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, s.a, s.b);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "profile event"); continue; }
+        int i = 0;
+        for (; i < n; ++i)
+            if (s.name == stats[i].name) break;
+        if (i == n) {
+            if (n >= max_stats || !stats) continue;
+            memset(&stats[n], 0, sizeof(SfaKernelStat));
+            strncpy(stats[n].name, s.name.c_str(), sizeof(stats[n].name) - 1);
+            ++n;
+        }
+        stats[i].launches += 1;
+        stats[i].total_ms += ms;
+    }
+    for (ProfSpan& s : g_spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    g_spans.clear();
+    return rc == SFA_OK ? n : rc;
+}
 
 namespace {
 

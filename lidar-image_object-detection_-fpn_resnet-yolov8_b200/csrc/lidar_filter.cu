@@ -149,9 +149,9 @@ extern "C" int sfa_filter_lidar(const float* pts, int64_t n, const SfaBevParams*
     int64_t blocks = (n + kPerCta - 1) / kPerCta;
     uint32_t* counts = static_cast<uint32_t*>(workspace);
     const float4* in = reinterpret_cast<const float4*>(pts);
-    filter_count_kernel<<<(unsigned)blocks, kThreads, 0, stream>>>(in, n, box, counts);
-    filter_scan_kernel<<<1, 1024, 0, stream>>>(counts, blocks, out_count);
-    filter_scatter_kernel<<<(unsigned)blocks, kThreads, 0, stream>>>(in, n, box, counts, reinterpret_cast<float4*>(out_pts));
+    SFA_LAUNCH("filter_count", stream, filter_count_kernel<<<(unsigned)blocks, kThreads, 0, stream>>>(in, n, box, counts));
+    SFA_LAUNCH("filter_scan", stream, filter_scan_kernel<<<1, 1024, 0, stream>>>(counts, blocks, out_count));
+    SFA_LAUNCH("filter_scatter", stream, filter_scatter_kernel<<<(unsigned)blocks, kThreads, 0, stream>>>(in, n, box, counts, reinterpret_cast<float4*>(out_pts)));
     SFA_CUDA_TRY(cudaGetLastError());
     return SFA_OK;
 }

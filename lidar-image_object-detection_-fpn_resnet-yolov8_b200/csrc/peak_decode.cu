@@ -382,7 +382,9 @@ int launch_decode(DecodeArgs a, cudaStream_t stream) {
     auto launch = [&](auto kernel) -> int {
         if (smem > 48 * 1024)
             SFA_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SFA_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, a));
+        cudaError_t err = cudaSuccess;
+        SFA_LAUNCH("peak_decode", stream, err = cudaLaunchKernelEx(&cfg, kernel, a));
+        SFA_CUDA_TRY(err);
         return SFA_OK;
     };
     if (smem > 200 * 1024 || n_max > 96ll * kThreads) {
@@ -429,7 +431,7 @@ extern "C" int sfa_nms(const float* heat, int32_t planes, int32_t h, int32_t w, 
     size_t total = (size_t)planes * h * w;
     size_t blocks = (total + 255) / 256;
     if (blocks > (size_t)kNumSMs * 16) blocks = (size_t)kNumSMs * 16;
-    nms_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(heat, planes, h, w, out);
+    SFA_LAUNCH("nms", (cudaStream_t)stream, nms_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(heat, planes, h, w, out));
     SFA_CUDA_TRY(cudaGetLastError());
     return SFA_OK;
 }
@@ -441,9 +443,10 @@ extern "C" int sfa_post_process(const float* det, int32_t B, int32_t K, int32_t 
     int n = B * K;
     if (n == 0) return SFA_OK;
     SFA_REQUIRE(det && out && cls && keep, "NULL pointer argument");
-    post_process_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(det, n, num_classes, down_ratio, bound_size_y,
-                                                                           bev_width, bound_size_x, bev_height,
-                                                                           peak_thresh, out, cls, keep);
+    SFA_LAUNCH("post_process", (cudaStream_t)stream,
+               post_process_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+                   det, n, num_classes, down_ratio, bound_size_y, bev_width, bound_size_x, bev_height, peak_thresh, out,
+                   cls, keep));
     SFA_CUDA_TRY(cudaGetLastError());
     return SFA_OK;
 }

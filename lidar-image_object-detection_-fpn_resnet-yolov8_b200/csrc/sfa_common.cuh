@@ -27,6 +27,21 @@ int cuda_fail(cudaError_t e, const char* what);
         }                                      \
     } while (0)
 
+// ---- launch accounting / optional per-kernel event timing (host_pipeline.cu) ----
+void note_launch();
+bool profiling_on();
+void profile_mark(const char* name, cudaStream_t stream, bool begin);
+
+// Wraps one kernel launch statement: counts it and, while profiling, brackets it with events.
+#define SFA_LAUNCH(name, stream, ...)                                       \
+    do {                                                                    \
+        const bool _prof = ::sfa::profiling_on();                           \
+        if (_prof) ::sfa::profile_mark(name, stream, true);                 \
+        __VA_ARGS__;                                                        \
+        ::sfa::note_launch();                                               \
+        if (_prof) ::sfa::profile_mark(name, stream, false);                \
+    } while (0)
+
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
 // ---- streaming memory access (data a CTA touches exactly once: keep it out of L1) ----

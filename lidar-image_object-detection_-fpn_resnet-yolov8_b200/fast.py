@@ -104,22 +104,53 @@ def filter_lidar_device(points, geom: BevGeometry):
     return out[: int(count.item())]
 
 
-def post_process_dense(detections, num_classes=3, down_ratio=4, peak_thresh=0.2, cnf=None):
+def decode_device(hm_cen, cen_offset, direction, z_coor, dim, K=40, out=None, inds=None):
+    """decode (utils/evaluation_utils.py:77-105) on CUDA float32 NCHW-contiguous heads, writing into
+    `out` [B,K,10] (allocated when None) — no allocation, copy or sync when `out` is given, so the
+    call can be captured in a CUDA graph.  `inds` optional int64 [B,K] receives the spatial indices."""
+    lib = _lib.load()
+    for name, t in (("hm_cen", hm_cen), ("direction", direction), ("z_coor", z_coor), ("dim", dim)):
+        _require_cuda(t, name)
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise TypeError("%s must be contiguous float32" % name)
+    if cen_offset is not None and (not cen_offset.is_cuda or cen_offset.dtype != torch.float32 or
+                                   not cen_offset.is_contiguous()):
+        raise TypeError("cen_offset must be a contiguous float32 CUDA tensor or None")
+    B, C, h, w = hm_cen.shape
+    if out is None:
+        out = torch.empty((B, K, 10), dtype=torch.float32, device=hm_cen.device)
+    elif out.shape != (B, K, 10) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("out must be contiguous float32 [B,K,10]")
+    with torch.cuda.device(hm_cen.device):
+        rc = lib.sfa_decode(_ptr(hm_cen), _ptr(cen_offset), _ptr(direction), _ptr(z_coor), _ptr(dim), B, C, h, w, K,
+                            _ptr(out), _ptr(inds), _stream_ptr(hm_cen.device))
+    if rc != 0:
+        # torch.topk raises RuntimeError when K > h*w (evaluation_utils.py:50): same exception type
+        raise RuntimeError("decode: " + _lib.last_error())
+    return out
+
+
+def post_process_dense(detections, num_classes=3, down_ratio=4, peak_thresh=0.2, cnf=None, out=None):
     """Dense post_processing (utils/evaluation_utils.py:112-163) on CUDA detections [B,K,10]:
-    returns (rows [B,K,8] f32, cls [B,K] i32, keep [B,K] bool), all on the device."""
+    returns (rows [B,K,8] f32, cls [B,K] i32, keep [B,K] u8/bool), all on the device.  With
+    `out=(rows, cls, keep_u8)` nothing is allocated (graph-capturable) and keep stays uint8."""
     from .config import kitti_config
     cnf = kitti_config if cnf is None else cnf
     lib = _lib.load()
     _require_cuda(detections, "detections")
-    det = detections.contiguous().float()
+    det = detections if (detections.dtype == torch.float32 and detections.is_contiguous()) else detections.contiguous().float()
     B, K = det.shape[0], det.shape[1]
-    rows = torch.empty((B, K, 8), dtype=torch.float32, device=det.device)
-    cls = torch.empty((B, K), dtype=torch.int32, device=det.device)
-    keep = torch.empty((B, K), dtype=torch.uint8, device=det.device)
-    _lib.check(lib.sfa_post_process(_ptr(det), B, K, int(num_classes), float(down_ratio), float(cnf.bound_size_y),
-                                    float(cnf.BEV_WIDTH), float(cnf.bound_size_x), float(cnf.BEV_HEIGHT),
-                                    float(peak_thresh), _ptr(rows), _ptr(cls), _ptr(keep), _stream_ptr(det.device)))
-    return rows, cls, keep.bool()
+    if out is None:
+        rows = torch.empty((B, K, 8), dtype=torch.float32, device=det.device)
+        cls = torch.empty((B, K), dtype=torch.int32, device=det.device)
+        keep = torch.empty((B, K), dtype=torch.uint8, device=det.device)
+    else:
+        rows, cls, keep = out
+    with torch.cuda.device(det.device):
+        _lib.check(lib.sfa_post_process(_ptr(det), B, K, int(num_classes), float(down_ratio), float(cnf.bound_size_y),
+                                        float(cnf.BEV_WIDTH), float(cnf.bound_size_x), float(cnf.BEV_HEIGHT),
+                                        float(peak_thresh), _ptr(rows), _ptr(cls), _ptr(keep), _stream_ptr(det.device)))
+    return (rows, cls, keep.bool()) if out is None else (rows, cls, keep)
 
 
 class HostPipeline:

@@ -100,13 +100,9 @@ def decode(hm_cen, cen_offset, direction, z_coor, dim, K=40):
         except _lib.SfaError as e:
             raise RuntimeError(str(e))
         return torch.from_numpy(det)
-    hm, dr, zc, dm = _f32c(hm_cen), _f32c(direction), _f32c(z_coor), _f32c(dim)
+    from ..fast import decode_device
     off = _f32c(cen_offset) if cen_offset is not None else None
-    det = torch.empty((B, K, 10), dtype=torch.float32, device=hm.device)
-    with torch.cuda.device(hm.device):
-        _raise_like_topk(lib.sfa_decode(_p(hm), _p(off), _p(dr), _p(zc), _p(dm), B, C, h, w, K, _p(det),
-                                        ctypes.c_void_p(0), _stream(hm)))
-    return det
+    return decode_device(_f32c(hm_cen), off, _f32c(direction), _f32c(z_coor), _f32c(dim), K=K)
 
 
 def get_yaw(direction):

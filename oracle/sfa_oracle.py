@@ -377,18 +377,26 @@ def synth_sweep(seed, n=120_000, geom: Geometry = KITTI, kind="uniform"):
 
 
 def synth_heads(seed, B=1, C=3, h=152, w=152, tie_free=False):
-    """Heads(seed) of SURVEY.md §8d: hm/off through _sigmoid, dir/z/dim raw randn.
+    """Heads(seed) of SURVEY.md §8d, in the value range every reference caller feeds decode with:
+    hm / cen_offset are post-_sigmoid, i.e. inside [1e-4, 1-1e-4] (test.py:150,167); dir/z/dim raw.
+    Only exactly-rounded operations are used (uniform draw, one multiply, one add) so that the same
+    seed gives the same bits on every host — torch's CPU sigmoid differs in the last ulp with the
+    thread count, which would unpin the committed fixtures.
     tie_free maps a random permutation onto distinct float32 values in (1e-4, 1-1e-4) so that
     top-K indices are uniquely defined (SURVEY.md §8c parity rules)."""
     g = torch.Generator().manual_seed(int(seed))
+
+    def unit(*shape):
+        return torch.rand(*shape, generator=g) * (1 - 2e-4) + 1e-4
+
     if tie_free:
         n = C * h * w
-        base = torch.linspace(1.5e-4, 1 - 1.5e-4, n, dtype=torch.float64).float()
+        base = (torch.arange(n, dtype=torch.float64) * ((1 - 3e-4) / max(n - 1, 1)) + 1.5e-4).float()
         assert torch.unique(base).numel() == n
         hm = torch.stack([base[torch.randperm(n, generator=g)] for _ in range(B)]).view(B, C, h, w).contiguous()
     else:
-        hm = _sigmoid(torch.randn(B, C, h, w, generator=g))
-    off = _sigmoid(torch.randn(B, 2, h, w, generator=g))
+        hm = unit(B, C, h, w)
+    off = unit(B, 2, h, w)
     direction = torch.randn(B, 2, h, w, generator=g)
     z = torch.randn(B, 1, h, w, generator=g)
     dim = torch.randn(B, 3, h, w, generator=g)

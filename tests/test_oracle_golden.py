@@ -1,0 +1,150 @@
+"""CPU: the oracle (oracle/sfa_oracle.py) against the committed golden fixtures that
+tests/golden/make_golden.py produced by running the REFERENCE's own functions.  This is what pins
+the oracle; the GPU parity tests then compare the CUDA path with the oracle and with the same
+fixtures."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import sfa_oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GEOMS = {"kitti": O.KITTI, "kitti_back": O.KITTI_BACK, "argoverse": O.ARGOVERSE}
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def bev_small():
+    return np.load(os.path.join(GOLD, "bev_small.npz"))
+
+
+@pytest.fixture(scope="module")
+def decode_small():
+    return np.load(os.path.join(GOLD, "decode_small.npz"))
+
+
+def dense_from_sparse(z, tag, geom):
+    out = np.zeros(3 * geom.BEV_HEIGHT * geom.BEV_WIDTH, dtype=np.float64)
+    out[z[tag + "_nz"]] = z[tag + "_val"]
+    return out.reshape(3, geom.BEV_HEIGHT, geom.BEV_WIDTH)
+
+
+def test_bev_small_cases_both_formulations(bev_small):
+    z = bev_small
+    n = int(z["n_cases"])
+    assert n == 24
+    for c in range(n):
+        tag = "c%02d" % c
+        gname, kind = z[tag + "_meta"]
+        geom = GEOMS[str(gname)]
+        pts = z[tag + "_pts"]
+        want = dense_from_sparse(z, tag, geom)
+        filt = O.get_filtered_lidar(pts.copy(), geom.boundary)
+        assert filt.dtype == np.float32
+        assert np.array_equal(filt.view(np.uint32), z[tag + "_filt"].view(np.uint32)), (gname, kind)
+        port = O.makeBEVMap(filt, geom.boundary, geom)
+        assert port.dtype == np.float64 and np.array_equal(port.view(np.uint64), want.view(np.uint64)), (gname, kind)
+        scat = O.make_bev_scatter(pts, geom, True, np.float32)
+        assert np.array_equal(scat.view(np.uint32), want.astype(np.float32).view(np.uint32)), (gname, kind)
+        # makeBEVMap alone on the already filtered sweep (apply_filter=False path of the kernel)
+        scat2 = O.make_bev_scatter(filt, geom, False, np.float32)
+        assert np.array_equal(scat2.view(np.uint32), want.astype(np.float32).view(np.uint32)), (gname, kind)
+
+
+def test_bev_full_size_hashes():
+    with open(os.path.join(GOLD, "bev_hashes.json")) as f:
+        cases = json.load(f)
+    assert len(cases) >= 12
+    for c in cases:
+        geom = GEOMS[c["geom"]]
+        sweep = O.synth_sweep(c["seed"], c["n"], geom, c["kind"])
+        if sha(sweep) != c["input_sha256"]:
+            pytest.skip("numpy's generator produced a different stream than when the fixture was made")
+        filt = O.get_filtered_lidar(sweep.copy(), geom.boundary)
+        assert filt.shape[0] == c["filtered_rows"] and sha(filt) == c["filtered_sha256"]
+        scat = O.make_bev_scatter(sweep, geom, True, np.float32)
+        assert sha(scat) == c["bev_f32_sha256"], c
+        assert int(np.count_nonzero(scat[2])) == c["occupied"]
+        if c["n"] <= 120000 and c["kind"] in ("uniform", "zties", "bounds"):
+            assert sha(O.makeBEVMap(filt, geom.boundary, geom)) == c["bev_f64_sha256"], c
+
+
+def test_density_lut_is_invertible_and_saturates():
+    lut = O.density_lut64()
+    assert lut[0] == 0.0 and lut[63] == 1.0 and np.all(np.diff(lut) > 0)
+    assert np.all(np.diff(lut.astype(np.float32)) > 0)
+
+
+def _heads(z, tag):
+    return tuple(torch.from_numpy(z["%s_%s" % (tag, n)].copy()) for n in ("hm", "off", "dir", "z", "dim"))
+
+
+def test_decode_small_cases(decode_small):
+    z = decode_small
+    for cid in range(int(z["n_cases"])):
+        tag = "d%d" % cid
+        K = int(z[tag + "_K"])
+        hm, off, direction, zc, dim = _heads(z, tag)
+        assert np.array_equal(O._nms(hm.clone()).numpy().view(np.uint32), z[tag + "_nms"].view(np.uint32))
+        det = O.decode(hm.clone(), off, direction, zc, dim, K=K).numpy()
+        assert np.array_equal(det.view(np.uint32), z[tag + "_det"].view(np.uint32)), tag
+        if (tag + "_topk_inds") not in z:
+            continue
+        ts, ti, tc, ty, tx = O._topk(O._nms(hm.clone()), K=K)
+        assert np.array_equal(ti.numpy(), z[tag + "_topk_inds"])
+        assert np.array_equal(tc.numpy(), z[tag + "_topk_clses"])
+        assert np.array_equal(ts.numpy(), z[tag + "_topk_score"])
+        assert np.array_equal(ty.numpy(), z[tag + "_topk_ys"]) and np.array_equal(tx.numpy(), z[tag + "_topk_xs"])
+        det0 = O.decode(hm.clone(), None, direction, zc, dim, K=K).numpy()
+        assert np.array_equal(det0, z[tag + "_det_nooff"])
+        pp = O.post_processing(det.astype(np.float32), 3, 4, 0.2)
+        assert len(pp) == det.shape[0]
+        for i, d in enumerate(pp):
+            for j in range(3):
+                want = z["%s_pp_s%d_c%d" % (tag, i, j)]
+                got = np.asarray(d[j], dtype=np.float32).reshape(-1, 8)
+                assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (tag, i, j)
+        live = O.post_processing_live_semantics(det.astype(np.float32))
+        assert len(live) == 1
+        real = np.asarray(O.convert_det_to_real_values(pp[0]), dtype=np.float64).reshape(-1, 8)
+        assert np.array_equal(real, z[tag + "_real_s0"])
+
+
+def test_decode_full_size_hashes():
+    with open(os.path.join(GOLD, "decode_hashes.json")) as f:
+        cases = json.load(f)
+    for c in cases:
+        heads = O.synth_heads(c["seed"], B=c["B"], C=3, h=152, w=152, tie_free=c["tie_free"])
+        if sha(np.concatenate([t.numpy().ravel() for t in heads])) != c["input_sha256"]:
+            pytest.skip("torch's CPU generator produced a different stream than when the fixture was made")
+        hm, off, direction, zc, dim = heads
+        assert sha(O._nms(hm.clone()).numpy()) == c["nms_sha256"]
+        det = O.decode(hm.clone(), off.clone(), direction, zc, dim, K=c["K"]).numpy()
+        assert sha(O.canonical_detections(det)) == c["det_canonical_sha256"]
+        if c["adjacent_equal_scores"] == 0:
+            assert sha(det) == c["det_sha256"]
+
+
+def test_global_topk_equals_two_stage_topk_when_tie_free():
+    """The CUDA kernel selects the global top-K of C*h*w; the reference does per-class top-K then
+    top-K of the C*K candidates (evaluation_utils.py:47-62).  Equal when the K scores are distinct."""
+    hm = O.synth_heads(77, B=3, tie_free=True)[0]
+    ts, ti, tc, _, _ = O._topk(hm, K=50)
+    flat = hm.view(3, -1)
+    gs, gi = torch.topk(flat, 50)
+    assert torch.equal(gs, ts) and torch.equal(gi % (152 * 152), ti) and torch.equal((gi // (152 * 152)).int(), tc)
+
+
+def test_canonical_detections_orders_ties():
+    d = np.zeros((1, 4, 10), np.float32)
+    d[0, :, 0] = [0.9, 0.5, 0.5, 0.1]
+    d[0, :, 9] = [0, 2, 1, 0]
+    c = O.canonical_detections(d)
+    assert list(c[0, :, 9]) == [0, 1, 2, 0]
