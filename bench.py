@@ -270,7 +270,7 @@ def run_b200(args):
     for pts, heads in host_sets:
         dev_sets.append((torch.from_numpy(pts).to(dev).reshape(-1, 4), tuple(t.to(dev) for t in heads)))
     offsets = torch.arange(B + 1, dtype=torch.int64, device=dev) * N_POINTS
-    rast = fast.BevRasterizer(geom, max_batch=B, device=dev)
+    rast = fast.BevRasterizer(geom, max_batch=B, max_points=N_POINTS, device=dev)
     bev_out = torch.empty((B, 3, BEV_H, BEV_W), dtype=torch.float32, device=dev)
     det_out = torch.empty((B, TOPK, 10), dtype=torch.float32, device=dev)
     pp_out = (torch.empty((B, TOPK, 8), dtype=torch.float32, device=dev),
@@ -377,11 +377,12 @@ def run_b200(args):
             pl.bev(pts_pin.numpy(), offs_h, out=bev_pin.numpy())
             pl.decode(*[t.numpy() for t in heads_pin], out=det_pin.numpy())
 
+        e2e_steps = max(1, min(args.steps, 200))
         for _ in range(3):
             e2e_step()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(e2e_steps):
             e2e_step()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
@@ -391,8 +392,8 @@ def run_b200(args):
             dt = float(t.item())
         h2d = pts_pin.numel() * 4 + sum(t.numel() * 4 for t in heads_pin) + offs_h.nbytes
         d2h = bev_pin.numel() * 4 + det_pin.numel() * 4
-        e2e = {"value": round(B * args.steps * world / dt, 1), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": round(dt / args.steps * 1e3, 4),
+        e2e = {"value": round(B * e2e_steps * world / dt, 1), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": round(dt / e2e_steps * 1e3, 4), "steps": e2e_steps,
                "api": "sfa_pipeline_bev_host + sfa_pipeline_decode_host (pinned host sweeps/heads in, host BEV maps + "
                       "detections out)"}
         pl.close()

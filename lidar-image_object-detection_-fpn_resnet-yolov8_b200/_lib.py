@@ -16,7 +16,10 @@ class SfaBevParams(ctypes.Structure):
     """struct SfaBevParams of include/sfa_b200.h."""
     _fields_ = [("min_x", f32), ("max_x", f32), ("min_y", f32), ("max_y", f32), ("min_z", f32), ("max_z", f32),
                 ("discretization", f32), ("y_offset", f32), ("max_height", f32),
-                ("height", i32), ("width", i32), ("apply_filter", i32)]
+                ("height", i32), ("width", i32), ("apply_filter", i32), ("algorithm", i32)]
+
+
+BEV_AUTO, BEV_TILED, BEV_GLOBAL_ATOMIC = 0, 1, 2   # enum SfaBevAlgorithm
 
 
 class SfaKernelStat(ctypes.Structure):
@@ -37,7 +40,7 @@ PROTOTYPES = {
     "sfa_kernel_launches": (ctypes.c_uint64, []),
     "sfa_profile_begin": (ctypes.c_int, []),
     "sfa_profile_end": (ctypes.c_int, [ctypes.POINTER(SfaKernelStat), i32]),
-    "sfa_bev_workspace_bytes": (sz, [i32, ctypes.POINTER(SfaBevParams)]),
+    "sfa_bev_workspace_bytes": (sz, [i32, i64, ctypes.POINTER(SfaBevParams)]),
     "sfa_bev_workspace_init": (ctypes.c_int, [c_void_p, sz, c_void_p]),
     "sfa_bev_rasterize": (ctypes.c_int, [c_void_p, c_void_p, i32, i64, ctypes.POINTER(SfaBevParams), c_void_p,
                                          c_void_p, c_void_p, c_void_p, sz, c_void_p]),

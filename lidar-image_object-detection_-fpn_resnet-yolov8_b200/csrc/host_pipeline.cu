@@ -180,7 +180,7 @@ extern "C" SfaPipeline* sfa_pipeline_create(int32_t device, int32_t max_frames, 
         chk(cudaMalloc(&l.d_offsets, (pl->chunk + 1) * sizeof(int64_t)), "cudaMalloc offsets");
         chk(cudaMallocHost(&l.h_offsets, (pl->chunk + 1) * sizeof(int64_t)), "cudaMallocHost offsets");
         chk(cudaMalloc(&l.d_out, (size_t)pl->chunk * 3 * cells * sizeof(float)), "cudaMalloc out");
-        l.ws_bytes = sfa_bev_workspace_bytes(pl->chunk, p);
+        l.ws_bytes = sfa_bev_workspace_bytes(pl->chunk, max_points_per_frame, p);
         chk(cudaMalloc(&l.d_ws, l.ws_bytes), "cudaMalloc ws");
         if (ok && sfa_bev_workspace_init(l.d_ws, l.ws_bytes, l.stream) != SFA_OK) ok = false;
         if (head_ch) {

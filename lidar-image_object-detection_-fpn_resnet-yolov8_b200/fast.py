@@ -33,14 +33,15 @@ class BevRasterizer:
     """Stage A for batches of sweeps resident in HBM (replaces get_filtered_lidar + makeBEVMap,
     data_process/kitti_data_utils.py:228-241 and data_process/kitti_bev_utils.py:22-55)."""
 
-    def __init__(self, geom: BevGeometry, max_batch: int = 64, device=None):
+    def __init__(self, geom: BevGeometry, max_batch: int = 64, max_points: int = 131072, device=None):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("BevRasterizer needs a CUDA device (there is no CPU fallback)")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.geom = geom
         self.max_batch = int(max_batch)
-        nbytes = self.lib.sfa_bev_workspace_bytes(self.max_batch, ctypes.byref(geom.params))
+        self.max_points = int(max_points)
+        nbytes = self.lib.sfa_bev_workspace_bytes(self.max_batch, self.max_points, ctypes.byref(geom.params))
         if nbytes == 0:
             raise _lib.SfaError(-1, _lib.last_error() or "bad geometry")
         with torch.cuda.device(self.device):
@@ -64,6 +65,9 @@ class BevRasterizer:
             raise ValueError("points / offsets must be contiguous")
         B = offsets.numel() - 1
         g = self.geom
+        if int(max_points) > self.max_points:
+            raise ValueError("max_points %d exceeds the %d this rasteriser's workspace was sized for"
+                             % (int(max_points), self.max_points))
         if out is None:
             out = torch.empty((B, 3, g.height, g.width), dtype=torch.float32, device=self.device)
         elif out.shape != (B, 3, g.height, g.width) or out.dtype != torch.float32 or not out.is_contiguous():

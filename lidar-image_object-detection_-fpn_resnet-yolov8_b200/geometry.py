@@ -23,7 +23,7 @@ class BevGeometry:
     """One raster configuration.  `cnf` is a module/object with BEV_HEIGHT, BEV_WIDTH, DISCRETIZATION;
     `boundary` is the dict the reference passes around (minX..maxZ)."""
 
-    def __init__(self, boundary, cnf, apply_filter=True):
+    def __init__(self, boundary, cnf, apply_filter=True, algorithm=_lib.BEV_AUTO):
         self.boundary = dict(boundary)
         self.height = int(cnf.BEV_HEIGHT)
         self.width = int(cnf.BEV_WIDTH)
@@ -39,6 +39,8 @@ class BevGeometry:
         p.max_height = np.float32(float(np.abs(b["maxZ"] - b["minZ"])))    # kitti_bev_utils.py:43
         p.height, p.width = self.height, self.width
         p.apply_filter = 1 if apply_filter else 0
+        p.algorithm = int(algorithm)
+        self.algorithm = int(algorithm)
         self.params = p
         self.lut64 = density_lut64()
         self.lut32 = self.lut64.astype(np.float32)
@@ -46,12 +48,13 @@ class BevGeometry:
 
     def key(self):
         b = self.boundary
-        return (tuple(sorted(b.items())), self.height, self.width, self.discretization, self.apply_filter)
+        return (tuple(sorted(b.items())), self.height, self.width, self.discretization, self.apply_filter,
+                self.algorithm)
 
     @property
     def cells(self):
         return self.height * self.width
 
 
-def from_config(cnf, boundary=None, apply_filter=True):
-    return BevGeometry(cnf.boundary if boundary is None else boundary, cnf, apply_filter)
+def from_config(cnf, boundary=None, apply_filter=True, algorithm=_lib.BEV_AUTO):
+    return BevGeometry(cnf.boundary if boundary is None else boundary, cnf, apply_filter, algorithm)

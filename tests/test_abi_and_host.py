@@ -42,12 +42,15 @@ def test_version_and_host_only_entry_points(built_lib):
     lib = built_lib
     assert lib.sfa_version() == 100
     g = pkg("geometry").from_config(pkg("config.kitti_config"))
-    assert ctypes.sizeof(g.params) == 48          # struct SfaBevParams: 9 floats + 3 int32
-    n1 = lib.sfa_bev_workspace_bytes(1, ctypes.byref(g.params))
-    n64 = lib.sfa_bev_workspace_bytes(64, ctypes.byref(g.params))
-    assert n1 > 0 and n64 >= n1 and n64 < (1 << 30)
+    assert ctypes.sizeof(g.params) == 52          # struct SfaBevParams: 9 floats + 4 int32
+    n1 = lib.sfa_bev_workspace_bytes(1, 120000, ctypes.byref(g.params))
+    n64 = lib.sfa_bev_workspace_bytes(64, 120000, ctypes.byref(g.params))
+    assert n1 >= 64 * 120000 * 16 and n64 >= n1 and n64 < (4 << 30)
+    ga = pkg("geometry").from_config(pkg("config.kitti_config"), algorithm=pkg("_lib").BEV_GLOBAL_ATOMIC)
+    na = lib.sfa_bev_workspace_bytes(64, 120000, ctypes.byref(ga.params))
+    assert 608 * 608 * 12 <= na < (1 << 30)
     bad = pkg("_lib").SfaBevParams()
-    assert lib.sfa_bev_workspace_bytes(1, ctypes.byref(bad)) == 0
+    assert lib.sfa_bev_workspace_bytes(1, 1000, ctypes.byref(bad)) == 0
     assert b"BEV size" in lib.sfa_last_error()
     assert lib.sfa_filter_workspace_bytes(120000) >= 4
     # argument validation happens before any CUDA call

@@ -14,16 +14,21 @@ pytestmark = pytest.mark.gpu
 KINDS = ["uniform", "outside", "zties", "gridaligned", "bounds", "nonfinite", "onecell", "clustered"]
 
 
-def _geom(ogeom, apply_filter=True):
+AUTO, TILED, ATOMIC = 0, 1, 2   # enum SfaBevAlgorithm (include/sfa_b200.h)
+ALGOS = [pytest.param(TILED, id="tiled"), pytest.param(ATOMIC, id="atomic")]
+
+
+def _geom(ogeom, apply_filter=True, algorithm=AUTO):
     class Cnf:
         BEV_HEIGHT, BEV_WIDTH, DISCRETIZATION = ogeom.BEV_HEIGHT, ogeom.BEV_WIDTH, ogeom.DISCRETIZATION
-    return pkg("geometry").BevGeometry(ogeom.boundary, Cnf, apply_filter=apply_filter)
+    return pkg("geometry").BevGeometry(ogeom.boundary, Cnf, apply_filter=apply_filter, algorithm=algorithm)
 
 
-def _run_batch(cuda_device, sweeps, ogeom, apply_filter=True, max_batch=None):
+def _run_batch(cuda_device, sweeps, ogeom, apply_filter=True, max_batch=None, algorithm=AUTO):
     fast = pkg("fast")
-    rast = fast.BevRasterizer(_geom(ogeom, apply_filter), max_batch=max_batch or max(1, len(sweeps)), device=cuda_device)
     lens = [s.shape[0] for s in sweeps]
+    rast = fast.BevRasterizer(_geom(ogeom, apply_filter, algorithm), max_batch=max_batch or max(1, len(sweeps)),
+                              max_points=max(lens + [1]), device=cuda_device)
     offsets = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int64, device=cuda_device)
     allpts = np.concatenate(sweeps, 0) if sum(lens) else np.zeros((0, 4), np.float32)
     pts = torch.from_numpy(allpts).to(cuda_device)
@@ -43,12 +48,13 @@ def _assert_bit_exact(got, want, what):
     np.testing.assert_allclose(got, want, rtol=1e-6, atol=0)  # the contract's tolerance, trivially met
 
 
+@pytest.mark.parametrize("algorithm", ALGOS)
 @pytest.mark.parametrize("kind", KINDS)
 @pytest.mark.parametrize("n", [0, 1, 5000, 120000])
-def test_bev_single_sweep_bit_exact(cuda_device, kind, n):
+def test_bev_single_sweep_bit_exact(cuda_device, kind, n, algorithm):
     n = min(n, 100000) if kind == "onecell" else n
     sweep = O.synth_sweep(17, n, O.KITTI, kind) if n else np.zeros((0, 4), np.float32)
-    got, rast = _run_batch(cuda_device, [sweep], O.KITTI)
+    got, rast = _run_batch(cuda_device, [sweep], O.KITTI, algorithm=algorithm)
     want = O.make_bev_scatter(sweep, O.KITTI, True, np.float32)
     _assert_bit_exact(got[0], want, "%s n=%d" % (kind, n))
     assert rast.out_of_map_points() == 0
@@ -62,9 +68,10 @@ def test_bev_matches_lexsort_formulation(cuda_device):
     _assert_bit_exact(got[0], ref.astype(np.float32), "lexsort port")
 
 
-def test_bev_batch64_ragged_and_ring_reuse(cuda_device):
-    """BASELINE config[1] shape: 64 sweeps; ragged sizes; the scratch ring is reused 8 times, and the
-    same rasteriser is called twice (the workspace must come back clean)."""
+@pytest.mark.parametrize("algorithm", ALGOS)
+def test_bev_batch64_ragged_and_ring_reuse(cuda_device, algorithm):
+    """BASELINE config[1] shape: 64 sweeps; ragged sizes; the workspace ring is reused several times,
+    and the same geometry is run twice (the workspace must come back clean)."""
     rng = np.random.default_rng(5)
     sweeps = []
     for i in range(64):
@@ -72,14 +79,15 @@ def test_bev_batch64_ragged_and_ring_reuse(cuda_device):
         sweeps.append(O.synth_sweep(100 + i, n, O.KITTI, KINDS[i % len(KINDS)] if n <= 100000 else "uniform")
                       if n else np.zeros((0, 4), np.float32))
     for attempt in range(2):
-        got, rast = _run_batch(cuda_device, sweeps, O.KITTI)
+        got, rast = _run_batch(cuda_device, sweeps, O.KITTI, algorithm=algorithm)
         for i, s in enumerate(sweeps):
             _assert_bit_exact(got[i], O.make_bev_scatter(s, O.KITTI, True, np.float32), "frame %d" % i)
 
 
-def test_bev_second_call_same_workspace(cuda_device):
+@pytest.mark.parametrize("algorithm", ALGOS)
+def test_bev_second_call_same_workspace(cuda_device, algorithm):
     fast = pkg("fast")
-    rast = fast.BevRasterizer(_geom(O.KITTI), max_batch=4, device=cuda_device)
+    rast = fast.BevRasterizer(_geom(O.KITTI, algorithm=algorithm), max_batch=4, max_points=61000, device=cuda_device)
     for seed in (1, 2, 3):
         sweeps = [O.synth_sweep(seed * 10 + j, 50000 + 1000 * j, O.KITTI, "zties") for j in range(11)]
         lens = [s.shape[0] for s in sweeps]
@@ -90,39 +98,90 @@ def test_bev_second_call_same_workspace(cuda_device):
             _assert_bit_exact(got[i], O.make_bev_scatter(s, O.KITTI, True, np.float32), "seed %d frame %d" % (seed, i))
 
 
-def test_bev_back_boundary_negative_row_wrap(cuda_device):
+@pytest.mark.parametrize("algorithm", ALGOS)
+def test_bev_back_boundary_negative_row_wrap(cuda_device, algorithm):
     """boundary_back (config/kitti_config.py:36-43): x in [-50, 0] -> negative rows wrap (numpy
     negative indexing) — rows 1..607 occupied, row 0 only from x == 0."""
     sweep = O.synth_sweep(8, 80000, O.KITTI_BACK, "uniform")
-    got, _ = _run_batch(cuda_device, [sweep], O.KITTI_BACK)
+    got, _ = _run_batch(cuda_device, [sweep], O.KITTI_BACK, algorithm=algorithm)
     _assert_bit_exact(got[0], O.make_bev_scatter(sweep, O.KITTI_BACK, True, np.float32), "back")
 
 
+@pytest.mark.parametrize("algorithm", ALGOS)
 @pytest.mark.parametrize("kind", ["uniform", "zties", "outside"])
-def test_bev_argoverse_range_250k(cuda_device, kind):
+def test_bev_argoverse_range_250k(cuda_device, kind, algorithm):
     """BASELINE config[3]: Argoverse-range sweeps (~250k points, +-50 m, z in [-3, 5])."""
     sweep = O.synth_sweep(21, 250000, O.ARGOVERSE, kind)
-    got, _ = _run_batch(cuda_device, [sweep], O.ARGOVERSE)
+    got, _ = _run_batch(cuda_device, [sweep], O.ARGOVERSE, algorithm=algorithm)
     _assert_bit_exact(got[0], O.make_bev_scatter(sweep, O.ARGOVERSE, True, np.float32), "argoverse " + kind)
 
 
-def test_bev_without_filter_negative_z_and_nan_z(cuda_device):
+@pytest.mark.parametrize("algorithm", ALGOS)
+def test_bev_without_filter_negative_z_and_nan_z(cuda_device, algorithm):
     """makeBEVMap alone (apply_filter=0): z not shifted, may be negative; NaN z sorts last."""
     sweep = O.synth_sweep(9, 60000, O.KITTI, "zties")
     sweep[::97, 2] = np.nan
-    got, _ = _run_batch(cuda_device, [sweep], O.KITTI, apply_filter=False)
+    got, _ = _run_batch(cuda_device, [sweep], O.KITTI, apply_filter=False, algorithm=algorithm)
     want = O.make_bev_scatter(sweep, O.KITTI, apply_filter=False, dtype=np.float32)
     assert np.array_equal(got[0], want, equal_nan=True)
     assert np.array_equal(np.isnan(got[0]), np.isnan(want))
 
 
 def test_bev_odd_grid_scalar_finalize(cuda_device):
-    """H*W not a multiple of 4 takes the scalar finalize path."""
+    """H*W not a multiple of 4: AUTO falls back to the global-atomic path with its scalar finalize."""
     g = O.Geometry(boundary={"minX": 0, "maxX": 30, "minY": -15, "maxY": 15, "minZ": -2, "maxZ": 2},
                    BEV_HEIGHT=301, BEV_WIDTH=301)
     sweep = O.synth_sweep(4, 40000, g, "zties")
     got, _ = _run_batch(cuda_device, [sweep], g)
     _assert_bit_exact(got[0], O.make_bev_scatter(sweep, g, True, np.float32), "301x301")
+
+
+@pytest.mark.parametrize("geomspec", [(304, 304), (1000, 1000), (2400, 2400), (3000, 3000), (100, 36)])
+def test_bev_other_grids_tiled_band_plans(cuda_device, geomspec):
+    """Other map sizes exercise other band plans of the tiled path (fewer / more than 64 bands, a last
+    band that is partly outside the map; 2400^2 needs 979 bands) and, at 3000^2 (> 2^23 cells), the
+    automatic switch to the global-atomic path; 1000^2 is the grid the literal Argoverse DISCRETIZATION=0.1 implies (argoverse_config.py:10)."""
+    H, W = geomspec
+    g = O.Geometry(boundary={"minX": 0, "maxX": 40, "minY": -20, "maxY": 20, "minZ": -2, "maxZ": 2},
+                   BEV_HEIGHT=H, BEV_WIDTH=W, DISCRETIZATION=40 / H)
+    if W != H:   # keep y inside the map: the y range follows W cells of size 40/H
+        half = (40 / H) * W / 2
+        g = O.Geometry(boundary={"minX": 0, "maxX": 40, "minY": -half, "maxY": half, "minZ": -2, "maxZ": 2},
+                       BEV_HEIGHT=H, BEV_WIDTH=W, DISCRETIZATION=40 / H)
+    sweeps = [O.synth_sweep(70 + i, 50000, g, k) for i, k in enumerate(["zties", "uniform", "outside"])]
+    got, _ = _run_batch(cuda_device, sweeps, g)
+    for i, s in enumerate(sweeps):
+        _assert_bit_exact(got[i], O.make_bev_scatter(s, g, True, np.float32), "%dx%d frame %d" % (H, W, i))
+
+
+def test_bev_crowded_band_streams_records(cuda_device):
+    """More records in one band than its threads hold in registers (8 x 512): the band kernel
+    re-reads them from L2 once per phase.  Also a single cell holding > 63 points (LUT saturation)."""
+    rng = np.random.default_rng(3)
+    n = 90000
+    b = O.KITTI.boundary
+    sweep = np.stack([rng.uniform(10.0, 10.7, n), rng.uniform(b["minY"], b["maxY"], n),
+                      np.round(rng.uniform(b["minZ"], b["maxZ"], n) * 16) / 16, rng.uniform(0, 1, n)], 1).astype(np.float32)
+    sweep[:500, 0] = 10.3
+    sweep[:500, 1] = 3.21
+    got, _ = _run_batch(cuda_device, [sweep], O.KITTI, algorithm=TILED)
+    _assert_bit_exact(got[0], O.make_bev_scatter(sweep, O.KITTI, True, np.float32), "crowded band")
+
+
+def test_bev_negative_zero_and_nan_payload_bits(cuda_device):
+    """Without the filter z is stored as given: a cell whose winner is -0.0 must output -0.0 / max_h
+    (= -0.0) like the reference, and +0.0 / -0.0 tie (lowest index wins)."""
+    sweep = np.zeros((6, 4), np.float32)
+    sweep[:, 0] = [1.0, 1.0, 5.0, 5.0, 9.0, 9.0]
+    sweep[:, 1] = 0.5
+    sweep[:, 2] = [-0.0, 0.0, 0.0, -0.0, -1.0, -0.0]
+    sweep[:, 3] = [0.1, 0.2, 0.3, 0.4, 0.5, 0.6]
+    for algorithm in (TILED, ATOMIC):
+        got, _ = _run_batch(cuda_device, [sweep], O.KITTI, apply_filter=False, algorithm=algorithm)
+        want = O.makeBEVMap(sweep, O.KITTI.boundary, O.KITTI).astype(np.float32)
+        assert np.array_equal(got[0], want)
+        if algorithm == TILED:   # the tiled path also keeps the sign bit of a zero winner
+            _assert_bit_exact(got[0], want, "signed zero")
 
 
 def test_bev_out_of_map_is_counted_not_written(cuda_device):

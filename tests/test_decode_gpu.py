@@ -91,7 +91,7 @@ def test_decode_other_K(cuda_device, K):
 @pytest.mark.parametrize("C,h,w", [(3, 200, 200), (1, 8, 8), (3, 16, 40), (5, 33, 7), (3, 152, 152)])
 def test_decode_other_shapes(cuda_device, C, h, w):
     """200x200 heads are what the Argoverse scripts feed decode (argoverse_test.py:669, 800x800 BEV)."""
-    K = min(50, h * w)
+    K = min(50, h * w // 16)   # >= K true peaks, so suppressed (zero, tied) cells never reach the top K
     heads = O.synth_heads(31, B=3, C=C, h=h, w=w, tie_free=True)
     want = O.decode(*[t.clone() for t in heads], K=K).numpy()
     g = _ev().decode(*_cuda(heads, cuda_device), K=K).cpu().numpy()
