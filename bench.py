@@ -286,13 +286,24 @@ def run_b200(args):
     for s in range(sets):
         step(s)
     torch.cuda.synchronize()
+    class _Eager:
+        def __init__(self, s):
+            self.s = s
+
+        def replay(self):
+            step(self.s)
+
     graphs, launches_per_step = [], 0
     cap_stream = torch.cuda.Stream(device=dev)
     for s in range(sets):
-        g = torch.cuda.CUDAGraph()
         n0 = lib.kernel_launches()
-        with torch.cuda.graph(g, stream=cap_stream):
-            step(s)
+        if args.eager:
+            g = _Eager(s)
+            g.replay()
+        else:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=cap_stream):
+                step(s)
         launches_per_step = lib.kernel_launches() - n0
         graphs.append(g)
 
@@ -305,7 +316,7 @@ def run_b200(args):
     with ClockSampler(local_rank) as clocks:
         # warm-up: at least W (>= 3) steps and at least 0.5 s, so clocks settle and get sampled under load
         n_warm, t_w = 0, time.monotonic()
-        while n_warm < max(args.warmup, 3) or time.monotonic() - t_w < 0.5:
+        while n_warm < max(args.warmup, 3) or (not args.eager and time.monotonic() - t_w < 0.5):
             graphs[n_warm % sets].replay()
             n_warm += 1
             if n_warm % 16 == 0:
@@ -408,7 +419,7 @@ def run_b200(args):
                                    % (B, N_POINTS, B, TOPK, HEAD_C, HEAD_H, HEAD_W),
                        "frames_per_step_per_gpu": B, "l2_policy": "inputs rotate over %d distinct batches (%.0f MB) > L2" %
                        (sets, sets * B * (16 * N_POINTS + 44 * HEAD_H * HEAD_W) / 1e6),
-                       "cuda_graph": True, "sharding": "frames, no collective on the data path"},
+                       "cuda_graph": not args.eager, "sharding": "frames, no collective on the data path"},
             "gpu_launches": int(launches_per_step * args.steps),
             "e2e": e2e, "roofline": roofline, "roofline_path": roofline_path, "kernels": kern,
             "cpu_baseline": cpu_baseline, "clocks": clocks.summary(t_begin, t_end),
@@ -459,6 +470,9 @@ def main():
     ap.add_argument("--sets", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true",
+                    help="profiling aid (ncu): plain launches instead of CUDA-graph replays, exactly W warm-up steps; "
+                         "the printed value is not a bench number")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = 4 if args.steps is None else args.steps

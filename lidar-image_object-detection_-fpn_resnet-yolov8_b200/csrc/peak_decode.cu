@@ -7,16 +7,20 @@
 //   decode :77-105  assembly of [B, K, 10]
 //   post_processing :112-163 ("evaluation_utils copy.py":112-143 per-sample semantics), dense form
 //
-// One kernel, one thread-block CLUSTER of kSlabs CTAs per frame:
-//   - each CTA owns a slab of rows of all C classes: it stages slab + halo in shared memory with
-//     coalesced loads, applies the 3x3 peak-keep there, and turns every value into an orderable
-//     32-bit key;
-//   - exact top-K of the slab by an 8-bit MSB-first radix select over shared memory (4 passes,
-//     warp-aggregated histogram updates), ties at the K-th value resolved toward the lower index;
-//   - the K survivors of every CTA go to the cluster leader's shared memory through DSMEM as
-//     64-bit (key << 32 | ~linear_index) words; the leader bitonic-sorts the kSlabs*K candidates
-//     and gathers the 8 regression values per detection straight from the NCHW heads (one 32-B
-//     sector each — no NHWC transpose).
+// One kernel, one thread-block CLUSTER of S (<= 8) CTAs per frame:
+//   - each CTA owns a slab of rows of all C classes: it stages slab + halo rows in shared memory
+//     with 16-B coalesced loads, applies the 3x3 peak-keep there and stores every value as an
+//     orderable 32-bit key in a second shared array;
+//   - exact top-K of the slab by an 8-bit MSB-first radix select over those keys (4 passes; the
+//     histogram updates peel the warp's two most common bins first, so the huge tie groups a
+//     heat map has after NMS — suppressed cells are all 0, clamped sigmoids plateau at 1e-4 — cost
+//     one shared atomic per warp instead of 32 serialised ones); ties at the K-th value resolve
+//     toward the lower index;
+//   - the slab's K survivors are ordered locally (rank by counting) and sent to the cluster
+//     leader's shared memory through DSMEM as 64-bit (key << 32 | ~linear_index) words; the leader
+//     merges the S sorted lists (own position + one binary search per other list) and gathers the
+//     8 regression values per detection straight from the NCHW heads (one 32-B sector each — no
+//     NHWC transpose).
 // The heat map is read from HBM exactly once; nothing intermediate is written to HBM.
 //
 // Tie rule (torch.topk leaves it implementation-defined): equal scores are ordered by lower class,
@@ -24,17 +28,21 @@
 #include "sfa_common.cuh"
 
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 namespace cg = cooperative_groups;
 
 namespace sfa {
 namespace {
 
-constexpr int kSlabs = 8;          // CTAs per cluster (portable maximum)
-constexpr int kThreads = 256;
+constexpr int kMaxSlabs = 8;       // CTAs per cluster (portable maximum)
+constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxK = 128;
+constexpr int kListCap = 3072;             // compact list of positive cells per slab (u16 entries)
 constexpr uint32_t kNanKey = 0xFFFFFFFFu;  // torch.topk ranks NaN above everything
+constexpr size_t kSmemTarget = 80 * 1024;  // two CTAs per SM with room to spare
+constexpr size_t kSmemLimit = 200 * 1024;
 
 struct DecodeArgs {
     const float* hm;      // [B,C,h,w]
@@ -43,8 +51,9 @@ struct DecodeArgs {
     const float* zc;      // [B,1,h,w]
     const float* dim;     // [B,3,h,w]
     int B, C, h, w, K;
-    int rows_per_slab;
+    int slabs, rows_per_slab;
     int do_nms;
+    int vec4;             // hm is 16-B aligned and w % 4 == 0
     float* det;           // [B,K,10] or null
     int64_t* inds;        // [B,K] or null
     // _topk outputs (all null for decode)
@@ -56,18 +65,34 @@ __device__ __forceinline__ float nanmax(float a, float b) {
     return (a != a) ? a : ((b != b) ? b : fmaxf(a, b));
 }
 
-// EPT = elements per thread held in registers between the NMS read phase and the in-place key write.
-template <int EPT>
+// hist[bin] += 1 for every active lane.  The warp's (up to) two most common bins are added by one
+// lane each; whatever is left goes lane by lane.  Must be called by all 32 lanes.
+__device__ __forceinline__ void hist_add(unsigned int* hist, bool active, uint32_t bin, int lane) {
+    unsigned remaining = __ballot_sync(0xFFFFFFFFu, active);
+#pragma unroll
+    for (int round = 0; round < 2; ++round) {
+        if (remaining == 0) return;   // warp-uniform
+        const int leader = __ffs(remaining) - 1;
+        const uint32_t lb = __shfl_sync(0xFFFFFFFFu, bin, leader);
+        const unsigned grp = __ballot_sync(0xFFFFFFFFu, active && bin == lb) & remaining;
+        if (lane == leader) atomicAdd(&hist[lb], (unsigned)__popc(grp));
+        remaining &= ~grp;
+    }
+    if (remaining & (1u << lane)) atomicAdd(&hist[bin], 1u);
+}
+
 __global__ void __launch_bounds__(kThreads)
 decode_kernel(DecodeArgs a) {
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ unsigned long long cand[kSlabs * kMaxK];  // only the leader's copy is used
+    __shared__ unsigned long long cand[kMaxSlabs * kMaxK];  // leader: S sorted lists
+    __shared__ unsigned long long surv[kMaxK];              // this slab's survivors, unordered
     __shared__ unsigned int hist[256];
-    __shared__ unsigned int sel_prefix, sel_need, n_cand, eq_running;
+    __shared__ unsigned int sel_prefix, sel_need, sel_eqpop, n_surv, eq_running, n_pos;
     __shared__ unsigned int warp_sums[kWarps];
 
     const int slab = cluster.block_rank();
+    const int S = a.slabs;
     const int b = blockIdx.y;
     const int C = a.C, h = a.h, w = a.w, K = a.K;
     const int hw = h * w;
@@ -75,71 +100,131 @@ decode_kernel(DecodeArgs a) {
     const int rows = max(0, min(a.rows_per_slab, h - r0));
     const int n = C * rows * w;                  // elements this CTA selects from
     const int trows = a.rows_per_slab + 2;       // tile rows incl. halo
-    float* tile = reinterpret_cast<float*>(smem_raw);          // [C][trows][w] raw heat
-    uint32_t* keys = reinterpret_cast<uint32_t*>(smem_raw);    // [n] after the in-place rewrite
+    const int tplane = trows * w;
+    // shared layout: tkeys [C][trows][w] u32 | okeys [C][rows_per_slab][w] u32 | plist [kListCap] u16
+    uint32_t* tkeys = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* okeys = tkeys + (size_t)C * tplane;
+    unsigned short* plist = reinterpret_cast<unsigned short*>(okeys + (size_t)C * a.rows_per_slab * w);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // every CTA of the cluster must be running before anyone writes into the leader's shared memory
     cluster.barrier_arrive();
 
-    // ---- stage slab + halo (rows r0-1 .. r0+rows) -------------------------------------------------
-    const float* hmb = a.hm + (size_t)b * C * hw;
-    const float ninf = __int_as_float(0xFF800000);
+    // ---- stage slab + halo rows (r0-1 .. r0+rows) as ORDERABLE KEYS ---------------------------------
+    // Per class the tile rows that exist in the map are one contiguous run of the NCHW plane, so the
+    // copy is linear; rows outside the map get key 0, below every real value (max_pool2d pads with
+    // -inf, whose key is 0x007FFFFF).  NaN maps to the largest key, so an integer max propagates it
+    // exactly like ATen's max_pool2d does.
+    if (tid == 0) { sel_prefix = 0; sel_need = (unsigned)min(K, n); sel_eqpop = 0; n_surv = 0; eq_running = 0; n_pos = 0; }
     if (rows > 0) {
-        const int tile_n = C * trows * w;
-        for (int e = tid; e < tile_n; e += kThreads) {
-            int c = e / (trows * w);
-            int rem = e - c * trows * w;
-            int tr = rem / w;
-            int x = rem - tr * w;
-            int y = r0 - 1 + tr;
-            float v = ninf;
-            if (y >= 0 && y < h && tr < rows + 2) v = __ldg(hmb + (size_t)c * hw + (size_t)y * w + x);
-            tile[e] = v;
+        const float* hmb = a.hm + (size_t)b * C * hw;
+        const int y_lo = r0 - 1;
+        const int tr_first = y_lo < 0 ? 1 : 0;                      // first tile row inside the map
+        const int tr_end = min(rows + 2, h - y_lo);                 // one past the last tile row inside the map
+        if (a.vec4) {
+            const int w4 = w >> 2, tplane4 = trows * w4;
+            const int lo4 = tr_first * w4, hi4 = tr_end * w4;
+            for (int c = 0; c < C; ++c) {
+                const float4* src = reinterpret_cast<const float4*>(hmb + (size_t)c * hw) + (ptrdiff_t)y_lo * w4;
+                uint4* dst = reinterpret_cast<uint4*>(tkeys + (size_t)c * tplane);
+                for (int i = tid; i < tplane4; i += kThreads) {
+                    uint4 k = make_uint4(0u, 0u, 0u, 0u);
+                    if (i >= lo4 && i < hi4) {
+                        const float4 v = __ldg(src + i);
+                        k = make_uint4(orderable_u32(v.x, kNanKey), orderable_u32(v.y, kNanKey),
+                                       orderable_u32(v.z, kNanKey), orderable_u32(v.w, kNanKey));
+                    }
+                    dst[i] = k;
+                }
+            }
+        } else {
+            const int lo = tr_first * w, hi = tr_end * w;
+            for (int c = 0; c < C; ++c) {
+                const float* src = hmb + (size_t)c * hw + (ptrdiff_t)y_lo * w;
+                uint32_t* dst = tkeys + (size_t)c * tplane;
+                for (int i = tid; i < tplane; i += kThreads)
+                    dst[i] = (i >= lo && i < hi) ? orderable_u32(__ldg(src + i), kNanKey) : 0u;
+            }
         }
     }
     __syncthreads();
 
-    // ---- 3x3 peak keep -> orderable keys (held in registers until the whole tile has been read) ---
-    uint32_t kreg[EPT];
-#pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-        int e = tid + j * kThreads;
-        kreg[j] = 0;
-        if (e < n) {
-            int c = e / (rows * w);
-            int rem = e - c * rows * w;
-            int r = rem / w;
-            int x = rem - r * w;
-            const float* t = tile + (c * trows + r + 1) * w + x;
-            float v = t[0];
-            float val = v;
-            if (a.do_nms) {
-                float m = v;
-#pragma unroll
-                for (int dy = -1; dy <= 1; ++dy) {
-                    const float* tr_ = t + dy * w;
-                    if (x > 0) m = nanmax(m, tr_[-1]);
-                    m = nanmax(m, tr_[0]);
-                    if (x < w - 1) m = nanmax(m, tr_[1]);
+    // ---- 3x3 peak keep in the key domain: one thread walks one (class, x) column down the slab ------
+    // heat * (maxpool(heat) == heat), evaluation_utils.py:21-26:
+    //   own is NaN             -> NaN           (NaN * keep)
+    //   max of the 3x3 == own  -> own           (keep = 1)
+    //   otherwise              -> own * 0 = 0, or NaN when own is +-inf
+    // Cells with a value above zero are remembered in a per-thread row bitmask and, after one
+    // block-wide scan of the per-thread counts, written to the compact list `plist`: in the common
+    // case they are the only cells that can reach the top K, and the select runs on that list.
+    {
+        const uint32_t kZero = 0x80000000u, kPosInf = 0xFF800000u, kNegInf = 0x007FFFFFu;
+        const int ncols = C * w;
+        const bool listable = a.rows_per_slab <= 64 && n <= 65535;
+        for (int col0 = 0; col0 < ncols; col0 += kThreads) {   // block-uniform trip count (barriers inside)
+            const int col = col0 + tid;
+            const bool valid = col < ncols && rows > 0;
+            const int c = valid ? col / w : 0;
+            const int x = valid ? col - c * w : 0;
+            const uint32_t* t = tkeys + (size_t)c * tplane + x;   // tile row 0 (halo above the slab)
+            const bool has_l = x > 0, has_r = x < w - 1;
+            unsigned long long posmask = 0ull;
+            if (valid) {
+                uint32_t own = t[w];
+                uint32_t h_prev = t[0], h_cur = own;
+                if (has_l) { h_prev = max(h_prev, t[-1]); h_cur = max(h_cur, t[w - 1]); }
+                if (has_r) { h_prev = max(h_prev, t[1]); h_cur = max(h_cur, t[w + 1]); }
+                uint32_t* orow = okeys + (size_t)c * rows * w + x;
+                for (int r = 0; r < rows; ++r) {
+                    const uint32_t* nx = t + (r + 2) * w;
+                    const uint32_t own_next = nx[0];
+                    uint32_t h_next = own_next;
+                    if (has_l) h_next = max(h_next, nx[-1]);
+                    if (has_r) h_next = max(h_next, nx[1]);
+                    uint32_t out = own;
+                    if (a.do_nms && own != kNanKey) {
+                        const uint32_t m = max(max(h_prev, h_cur), h_next);
+                        if (m != own) out = (own == kPosInf || own == kNegInf) ? kNanKey : kZero;
+                    }
+                    orow[r * w] = out;
+                    if (out > kZero) posmask |= 1ull << (r & 63);
+                    h_prev = h_cur; h_cur = h_next; own = own_next;
                 }
-                float keep = (m == v) ? 1.0f : 0.0f;
-                val = __fmul_rn(v, keep);  // heat * keep, evaluation_utils.py:26
             }
-            kreg[j] = orderable_u32(val, kNanKey);
+            // exclusive scan of the per-thread counts -> list offsets (column-major, then row order)
+            const unsigned cnt = listable ? (unsigned)__popcll(posmask) : 0u;
+            unsigned incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            if (lane == 31) warp_sums[warp] = incl;
+            __syncthreads();
+            unsigned at = n_pos + incl - cnt;
+            for (int q = 0; q < warp; ++q) at += warp_sums[q];
+            unsigned block_total = 0;
+            for (int q = 0; q < kWarps; ++q) block_total += warp_sums[q];
+            while (posmask && listable) {
+                const int r = __ffsll((long long)posmask) - 1;
+                posmask &= posmask - 1;
+                if (at < (unsigned)kListCap) plist[at] = (unsigned short)((c * rows + r) * w + x);
+                ++at;
+            }
+            __syncthreads();
+            if (tid == 0) n_pos = listable ? n_pos + block_total : 0xFFFFFFFFu;
+            __syncthreads();
         }
     }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-        int e = tid + j * kThreads;
-        if (e < n) keys[e] = kreg[j];
-    }
-    if (tid == 0) { sel_prefix = 0; sel_need = (unsigned)min(K, n); n_cand = 0; eq_running = 0; }
-    __syncthreads();
+
+    // The select runs over the compact list of positive cells when it holds at least K of them and
+    // did not overflow (then nothing <= 0 can be in the top K); otherwise over every cell of the slab.
+    const int kk = min(K, n);
+    const bool use_list = n_pos >= (unsigned)kk && n_pos <= (unsigned)kListCap && n <= 65535 && kk > 0;
+    const int n_items = use_list ? (int)n_pos : n;
+    auto item_elem = [&](int i) -> int { return use_list ? (int)plist[i] : i; };
 
     // ---- radix select: key of the K-th largest element of this slab --------------------------------
-    const int kk = min(K, n);
     unsigned int eq_total = 0;
     if (kk > 0) {
         for (int pass = 0; pass < 4; ++pass) {
@@ -148,15 +233,20 @@ decode_kernel(DecodeArgs a) {
             for (int i = tid; i < 256; i += kThreads) hist[i] = 0;
             __syncthreads();
             const uint32_t prefix = sel_prefix;
-            for (int base = 0; base < n; base += kThreads) {
-                int e = base + tid;
-                uint32_t bin = 256;  // sentinel: not counted
-                if (e < n) {
-                    uint32_t k = keys[e];
-                    if (((k ^ prefix) & himask) == 0) bin = (k >> shift) & 255u;
+            for (int base = 0; base < n_items; base += kThreads) {
+                const int i = base + tid;
+                bool active = false;
+                uint32_t bin = 0;
+                if (i < n_items) {
+                    const uint32_t k = okeys[item_elem(i)];
+                    active = ((k ^ prefix) & himask) == 0;
+                    bin = (k >> shift) & 255u;
                 }
-                unsigned m = __match_any_sync(0xFFFFFFFFu, bin);
-                if (bin < 256 && lane == (__ffs(m) - 1)) atomicAdd(&hist[bin], (unsigned)__popc(m));
+                if (use_list) {   // positives are spread over many bins: plain shared atomics
+                    if (active) atomicAdd(&hist[bin], 1u);
+                } else {          // whole slab: huge tie groups (zeros, plateaus) -> peel them
+                    hist_add(hist, active, bin, lane);
+                }
             }
             __syncthreads();
             if (warp == 0) {
@@ -180,7 +270,7 @@ decode_kernel(DecodeArgs a) {
                         if (cum < need && need <= cum + hloc[q]) {
                             sel_prefix = prefix | ((uint32_t)(255 - 8 * lane - q) << shift);
                             sel_need = need - cum;
-                            hist[0] = hloc[q];  // population of the chosen bin (read below after the last pass)
+                            sel_eqpop = hloc[q];  // population of the chosen bin
                             break;
                         }
                         cum += hloc[q];
@@ -189,47 +279,45 @@ decode_kernel(DecodeArgs a) {
             }
             __syncthreads();
         }
-        eq_total = hist[0];  // elements equal to the threshold key
+        eq_total = sel_eqpop;  // after the last pass: elements equal to the threshold key
     }
     const uint32_t thr = sel_prefix;
     const unsigned need_eq = sel_need;  // how many of the == thr elements belong to the top K
-    __syncthreads();
 
-    // ---- collect survivors into the leader's candidate table ---------------------------------------
-    cluster.barrier_wait();  // pairs with the arrive at the top: all CTAs of the cluster are alive
-    unsigned long long* lead_cand = cluster.map_shared_rank(cand, 0) + slab * kMaxK;
+    // ---- collect the slab's K survivors as composite words -----------------------------------------
     auto composite = [&](uint32_t k, int e) -> unsigned long long {
-        int c = e / (rows * w);
-        int rem = e - c * rows * w;
-        uint32_t lin = (uint32_t)(c * hw + r0 * w + rem);
+        const int c = e / (rows * w);
+        const int rem = e - c * rows * w;
+        const uint32_t lin = (uint32_t)(c * hw + r0 * w + rem);
         return ((unsigned long long)k << 32) | (unsigned long long)(0xFFFFFFFFu - lin);
     };
     if (kk > 0) {
         const bool take_all_eq = (eq_total == need_eq);
-        for (int e = tid; e < n; e += kThreads) {
-            uint32_t k = keys[e];
+        for (int i = tid; i < n_items; i += kThreads) {
+            const int e = item_elem(i);
+            const uint32_t k = okeys[e];
             if (k > thr || (take_all_eq && k == thr)) {
-                unsigned pos = atomicAdd(&n_cand, 1u);
-                lead_cand[pos] = composite(k, e);
+                const unsigned pos = atomicAdd(&n_surv, 1u);
+                surv[pos] = composite(k, e);
             }
         }
         if (!take_all_eq) {
             // more elements tie at the threshold than fit: take the need_eq lowest indices, in order
             for (int base = 0; base < n; base += kThreads) {
                 __syncthreads();
-                unsigned running = eq_running;
+                const unsigned running = eq_running;
                 if (running >= need_eq) break;
-                int e = base + tid;
-                bool eq = (e < n) && (keys[e] == thr);
-                unsigned bal = __ballot_sync(0xFFFFFFFFu, eq);
+                const int e = base + tid;
+                const bool eq = (e < n) && (okeys[e] == thr);
+                const unsigned bal = __ballot_sync(0xFFFFFFFFu, eq);
                 if (lane == 0) warp_sums[warp] = __popc(bal);
                 __syncthreads();
                 unsigned before = running;
                 for (int q = 0; q < warp; ++q) before += warp_sums[q];
-                unsigned rank = before + __popc(bal & ((1u << lane) - 1u));
+                const unsigned rank = before + __popc(bal & ((1u << lane) - 1u));
                 if (eq && rank < need_eq) {
-                    unsigned pos = atomicAdd(&n_cand, 1u);
-                    lead_cand[pos] = composite(thr, e);
+                    const unsigned pos = atomicAdd(&n_surv, 1u);
+                    surv[pos] = composite(thr, e);
                 }
                 if (tid == 0) {
                     unsigned tot = 0;
@@ -240,45 +328,50 @@ decode_kernel(DecodeArgs a) {
         }
     }
     __syncthreads();
-    // unused tail of this CTA's K slots: composite 0 sorts below every real candidate
-    for (int i = kk + tid; i < K; i += kThreads) lead_cand[i] = 0ull;
+
+    // ---- order the survivors (rank by counting; composites are distinct) and ship them to the leader
+    cluster.barrier_wait();  // pairs with the arrive at the top: all CTAs of the cluster are alive
+    unsigned long long* lead = cluster.map_shared_rank(cand, 0) + slab * kMaxK;
+    for (int i = tid; i < K; i += kThreads) {
+        if (i < kk) {
+            const unsigned long long v = surv[i];
+            int rank = 0;
+            for (int j = 0; j < kk; ++j) rank += (surv[j] > v) ? 1 : 0;
+            lead[rank] = v;
+        } else {
+            lead[i] = 0ull;  // padding sorts below every real candidate
+        }
+    }
     cluster.sync();  // DSMEM writes are visible to the leader; non-leaders may now exit
     if (slab != 0) return;
 
-    // ---- leader: sort kSlabs*K candidates (descending) and emit the frame's top K -------------------
-    // compact [slab][kMaxK] -> dense [kSlabs*K] at the front of the dynamic shared memory, padded to 2^m
-    unsigned long long* sorted = reinterpret_cast<unsigned long long*>(smem_raw);
-    const int total = kSlabs * K;
-    int P = 1;
-    while (P < total) P <<= 1;
-    for (int i = tid; i < P; i += kThreads) {
-        unsigned long long v = 0ull;
-        if (i < total) v = cand[(i / K) * kMaxK + (i % K)];
-        sorted[i] = v;
-    }
-    __syncthreads();
-    for (int size = 2; size <= P; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = tid; i < (P >> 1); i += kThreads) {
-                int lo = ((i / stride) * (stride << 1)) + (i % stride);
-                int hi = lo + stride;
-                bool desc = ((lo & size) == 0);
-                unsigned long long x = sorted[lo], y = sorted[hi];
-                if ((x < y) == desc) { sorted[lo] = y; sorted[hi] = x; }
+    // ---- leader: merge S descending lists; rank = position in own list + #greater in every other ---
+    for (int i = tid; i < S * K; i += kThreads) {
+        const int s = i / K;
+        const int j = i - s * K;
+        const unsigned long long v = cand[s * kMaxK + j];
+        if (v == 0ull) continue;
+        int rank = j;
+        for (int t = 0; t < S; ++t) {
+            if (t == s) continue;
+            const unsigned long long* lst = cand + t * kMaxK;
+            int lo = 0, hi = K;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (lst[mid] > v) lo = mid + 1; else hi = mid;
             }
-            __syncthreads();
+            rank += lo;
         }
-    }
-    for (int k = tid; k < K; k += kThreads) {
-        unsigned long long v = sorted[k];
-        uint32_t key = (uint32_t)(v >> 32);
-        uint32_t lin = 0xFFFFFFFFu - (uint32_t)v;
-        int c = lin / hw;
-        int sp = lin - c * hw;
-        int y = sp / w;
-        int x = sp - y * w;
-        float score = orderable_to_float(key);
-        size_t o = (size_t)b * K + k;
+        if (rank >= K) continue;
+        const int k = rank;
+        const uint32_t key = (uint32_t)(v >> 32);
+        const uint32_t lin = 0xFFFFFFFFu - (uint32_t)v;
+        const int c = lin / hw;
+        const int sp = lin - c * hw;
+        const int y = sp / w;
+        const int x = sp - y * w;
+        const float score = orderable_to_float(key);
+        const size_t o = (size_t)b * K + k;
         if (a.inds) a.inds[o] = sp;
         if (a.tk_score) {
             a.tk_score[o] = score;
@@ -352,48 +445,55 @@ post_process_kernel(const float* __restrict__ det, int n, int num_classes, float
     keep[i] = (c >= 0 && score > thresh) ? 1 : 0;            // :134, :152
 }
 
+size_t slab_smem_bytes(int C, int h, int w, int slabs) {
+    const int rps = (h + slabs - 1) / slabs;
+    return (size_t)C * (rps + 2) * w * sizeof(float) + (size_t)C * rps * w * sizeof(uint32_t) +
+           (size_t)kListCap * sizeof(unsigned short);
+}
+
 int launch_decode(DecodeArgs a, cudaStream_t stream) {
     SFA_REQUIRE(a.B >= 0 && a.C > 0 && a.h > 0 && a.w > 0, "bad head shape B=%d C=%d h=%d w=%d", a.B, a.C, a.h, a.w);
     SFA_REQUIRE(a.K > 0 && a.K <= kMaxK, "K=%d unsupported (1..%d)", a.K, kMaxK);
     // torch.topk(scores.view(B, C, -1), K) raises when K > h*w (evaluation_utils.py:50)
     SFA_REQUIRE((long long)a.K <= (long long)a.h * a.w, "K=%d exceeds h*w=%d (the reference's topk raises)", a.K, a.h * a.w);
-    SFA_REQUIRE((long long)a.C * a.h * a.w < 0xFFFFFFFFll, "head too large");
+    SFA_REQUIRE((long long)a.C * a.h * a.w < 0x7FFFFFFFll, "head too large");
     if (a.B == 0) return SFA_OK;
-    a.rows_per_slab = (a.h + kSlabs - 1) / kSlabs;
-    const long long n_max = (long long)a.C * a.rows_per_slab * a.w;
-    size_t tile_bytes = (size_t)a.C * (a.rows_per_slab + 2) * a.w * sizeof(float);
-    int P = 1;
-    while (P < kSlabs * a.K) P <<= 1;
-    size_t smem = tile_bytes > (size_t)P * 8 ? tile_bytes : (size_t)P * 8;
+    // slabs per frame: as few as keep a CTA's tile + keys within ~74 KB (3 CTAs / SM), more when the
+    // batch alone cannot fill the 148 SMs; at most the portable cluster size
+    int slabs = 1;
+    while (slabs < kMaxSlabs && slabs < a.h &&
+           (slab_smem_bytes(a.C, a.h, a.w, slabs) > kSmemTarget || (long long)a.B * slabs < 2 * kNumSMs))
+        ++slabs;
+    if (const char* e = getenv("SFA_DECODE_SLABS")) {   // tuning aid
+        int v = atoi(e);
+        if (v >= 1 && v <= kMaxSlabs && v <= a.h) slabs = v;
+    }
+    a.slabs = slabs;
+    a.rows_per_slab = (a.h + slabs - 1) / slabs;
+    const size_t smem = slab_smem_bytes(a.C, a.h, a.w, slabs);
+    if (smem > kSmemLimit) {
+        set_error("head %dx%dx%d too large for the fused decode (%zu B of shared memory per slab)", a.C, a.h, a.w, smem);
+        return SFA_ERR_UNSUPPORTED;
+    }
+    a.vec4 = ((a.w & 3) == 0 && (reinterpret_cast<uintptr_t>(a.hm) & 15) == 0) ? 1 : 0;
 
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(kSlabs, a.B, 1);
+    cfg.gridDim = dim3(slabs, a.B, 1);
     cfg.blockDim = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kSlabs;
+    attr[0].val.clusterDim.x = slabs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-
-    auto launch = [&](auto kernel) -> int {
-        if (smem > 48 * 1024)
-            SFA_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cudaError_t err = cudaSuccess;
-        SFA_LAUNCH("peak_decode", stream, err = cudaLaunchKernelEx(&cfg, kernel, a));
-        SFA_CUDA_TRY(err);
-        return SFA_OK;
-    };
-    if (smem > 200 * 1024 || n_max > 96ll * kThreads) {
-        set_error("head %dx%dx%d too large for the fused decode (slab of %lld elements)", a.C, a.h, a.w, n_max);
-        return SFA_ERR_UNSUPPORTED;
-    }
-    if (n_max <= 36ll * kThreads) return launch(decode_kernel<36>);
-    if (n_max <= 64ll * kThreads) return launch(decode_kernel<64>);
-    return launch(decode_kernel<96>);
+    SFA_CUDA_TRY(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    cudaError_t err = cudaSuccess;
+    SFA_LAUNCH("peak_decode", stream, err = cudaLaunchKernelEx(&cfg, decode_kernel, a));
+    SFA_CUDA_TRY(err);
+    return SFA_OK;
 }
 
 }  // namespace
