@@ -60,6 +60,38 @@ def test_version_and_host_only_entry_points(built_lib):
     assert rc == -1
 
 
+@pytest.mark.parametrize("H,W", [(608, 608), (304, 304), (1000, 1000), (2400, 2400), (100, 36), (800, 800), (64, 64)])
+def test_band_plan_divides_exactly(built_lib, H, W):
+    """The tiled BEV kernels map a cell to its band with a multiply-shift; the constants the host
+    derives must reproduce integer division for every cell of the map."""
+    class Cnf:
+        BEV_HEIGHT, BEV_WIDTH, DISCRETIZATION = H, W, 50 / H
+    g = pkg("geometry").BevGeometry(O.KITTI.boundary, Cnf)
+    nb, cpb, shift = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    magic = ctypes.c_uint32()
+    rc = built_lib.sfa_bev_band_plan(ctypes.byref(g.params), ctypes.byref(nb), ctypes.byref(cpb), ctypes.byref(magic),
+                                     ctypes.byref(shift))
+    assert rc == 1
+    cells = np.arange(H * W, dtype=np.uint64)
+    assert cpb.value % 4 == 0 and cpb.value <= 5888 and nb.value * cpb.value >= H * W > (nb.value - 1) * cpb.value
+    q = ((cells * np.uint64(magic.value)) >> np.uint64(32)) >> np.uint64(shift.value)
+    assert np.array_equal(q, cells // np.uint64(cpb.value))
+    if (H, W) == (608, 608):
+        assert (nb.value, cpb.value) == (64, 5776)
+
+
+def test_band_plan_falls_back_to_global_atomic(built_lib):
+    class Cnf:
+        BEV_HEIGHT, BEV_WIDTH, DISCRETIZATION = 301, 301, 50 / 301
+    g = pkg("geometry").BevGeometry(O.KITTI.boundary, Cnf)
+    assert built_lib.sfa_bev_band_plan(ctypes.byref(g.params), None, None, None, None) == 0   # H*W % 4 != 0
+    Cnf.BEV_HEIGHT = Cnf.BEV_WIDTH = 3000
+    g = pkg("geometry").BevGeometry(O.KITTI.boundary, Cnf)
+    assert built_lib.sfa_bev_band_plan(ctypes.byref(g.params), None, None, None, None) == 0   # > 2^23 cells
+    g = pkg("geometry").BevGeometry(O.KITTI.boundary, Cnf, algorithm=pkg("_lib").BEV_TILED)
+    assert built_lib.sfa_bev_band_plan(ctypes.byref(g.params), None, None, None, None) == -1  # cannot be forced
+
+
 def test_geometry_float32_rounding_matches_numpy_promotion():
     cnf = pkg("config.kitti_config")
     g = pkg("geometry").from_config(cnf)

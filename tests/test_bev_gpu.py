@@ -154,6 +154,19 @@ def test_bev_other_grids_tiled_band_plans(cuda_device, geomspec):
         _assert_bit_exact(got[i], O.make_bev_scatter(s, g, True, np.float32), "%dx%d frame %d" % (H, W, i))
 
 
+@pytest.mark.parametrize("algorithm", ALGOS)
+def test_bev_max_height_not_a_power_of_two(cuda_device, algorithm):
+    """maxZ - minZ = 3.0: the height plane needs the true fp32 division (for 4.0 / 8.0 the kernel
+    multiplies by the exact reciprocal instead)."""
+    g = O.Geometry(boundary={"minX": 0, "maxX": 50, "minY": -25, "maxY": 25, "minZ": -1.0, "maxZ": 2.0})
+    sweeps = [O.synth_sweep(90 + i, 60000, g, k) for i, k in enumerate(["uniform", "zties"])]
+    got, _ = _run_batch(cuda_device, sweeps, g, algorithm=algorithm)
+    for i, s in enumerate(sweeps):
+        _assert_bit_exact(got[i], O.make_bev_scatter(s, g, True, np.float32), "max_h=3 frame %d" % i)
+    ref = O.makeBEVMap(O.get_filtered_lidar(sweeps[0].copy(), g.boundary), g.boundary, g)
+    _assert_bit_exact(got[0], ref.astype(np.float32), "max_h=3 vs lexsort port")
+
+
 def test_bev_crowded_band_streams_records(cuda_device):
     """More records in one band than its threads hold in registers (8 x 512): the band kernel
     re-reads them from L2 once per phase.  Also a single cell holding > 63 points (LUT saturation)."""
