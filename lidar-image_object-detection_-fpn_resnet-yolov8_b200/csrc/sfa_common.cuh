@@ -57,6 +57,24 @@ __device__ __forceinline__ void st_stream_f4(float4* p, const float4& v) {
                  : "memory");
 }
 
+// ---- TMA bulk copies (cp.async.bulk, 1-D, no tensor map) ----------------------------------------
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+// Generic-proxy writes to shared memory (st.shared, atom.shared) -> visible to the async proxy.
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// shared::cta -> global, `bytes` a multiple of 16, both addresses 16-B aligned; joins the thread's bulk group.
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr_u32(ssrc)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk groups of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... have completed entirely
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- order-preserving float -> uint32 maps -------------------------------------------------------
 // Total order of the float VALUES (-0.0 == +0.0); `nan_key` is where NaN goes.
 __device__ __forceinline__ uint32_t orderable_u32(float f, uint32_t nan_key) {

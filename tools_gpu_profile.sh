@@ -12,6 +12,6 @@ if [ "${3:-}" = "list" ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
   echo "launch list rc=$?"
 fi
-ncu --set full --clock-control none --import-source on -k regex:"$PAT" -s "${SKIP:-24}" -c "$COUNT" -f -o gpurun_out/prof $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --cache-control ${CACHE:-all} --import-source on -k regex:"$PAT" -s "${SKIP:-24}" -c "$COUNT" -f -o gpurun_out/prof $CMD > gpurun_out/ncu_full.log 2>&1
 echo "full capture rc=$?"
 tail -2 gpurun_out/ncu_full.log
