@@ -50,10 +50,12 @@ PROTOTYPES = {
     "sfa_filter_lidar": (ctypes.c_int, [c_void_p, i64, ctypes.POINTER(SfaBevParams), c_void_p, c_void_p, c_void_p,
                                         sz, c_void_p]),
     "sfa_nms": (ctypes.c_int, [c_void_p, i32, i32, i32, c_void_p, c_void_p]),
+    "sfa_decode_workspace_bytes": (sz, [i32, i32, i32, i32, i32]),
+    "sfa_decode_workspace_init": (ctypes.c_int, [c_void_p, sz, c_void_p]),
     "sfa_topk": (ctypes.c_int, [c_void_p, i32, i32, i32, i32, i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                c_void_p]),
+                                c_void_p, sz, c_void_p]),
     "sfa_decode": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, i32, i32, i32, i32, i32, c_void_p,
-                                  c_void_p, c_void_p]),
+                                  c_void_p, c_void_p, sz, c_void_p]),
     "sfa_post_process": (ctypes.c_int, [c_void_p, i32, i32, i32, f32, f32, f32, f32, f32, f32, c_void_p, c_void_p,
                                         c_void_p, c_void_p]),
     "sfa_pipeline_create": (c_void_p, [i32, i32, i64, ctypes.POINTER(SfaBevParams), c_void_p, i32, i32, i32, i32]),

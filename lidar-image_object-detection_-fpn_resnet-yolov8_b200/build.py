@@ -45,6 +45,8 @@ def build(force=False, verbose=False):
         return LIB
     nvcc = find_nvcc()
     cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-shared", "-o", LIB]
+    if os.environ.get("SFA_DEBUG_TIMING") == "1":   # developer aid: per-phase cycle counters in bev_band
+        cmd += ["-DSFA_DEBUG_TIMING"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]

@@ -113,6 +113,8 @@ struct Lane {
     size_t ws_bytes = 0;
     float* d_heads = nullptr;        // hm | off | dir | z | dim for one chunk
     float* d_det = nullptr;
+    void* d_dec_ws = nullptr;        // sfa_decode workspace
+    size_t dec_ws_bytes = 0;
 };
 
 }  // namespace
@@ -134,7 +136,7 @@ static void pipeline_free(SfaPipeline* pl) {
     for (Lane& l : pl->lanes) {
         if (l.stream) cudaStreamSynchronize(l.stream);
         cudaFree(l.d_pts); cudaFree(l.d_offsets); cudaFreeHost(l.h_offsets); cudaFree(l.d_out);
-        cudaFree(l.d_ws); cudaFree(l.d_heads); cudaFree(l.d_det);
+        cudaFree(l.d_ws); cudaFree(l.d_heads); cudaFree(l.d_det); cudaFree(l.d_dec_ws);
         if (l.done) cudaEventDestroy(l.done);
         if (l.stream) cudaStreamDestroy(l.stream);
     }
@@ -186,6 +188,9 @@ extern "C" SfaPipeline* sfa_pipeline_create(int32_t device, int32_t max_frames, 
         if (head_ch) {
             chk(cudaMalloc(&l.d_heads, (size_t)pl->chunk * head_ch * h * w * sizeof(float)), "cudaMalloc heads");
             chk(cudaMalloc(&l.d_det, (size_t)pl->chunk * K * 10 * sizeof(float)), "cudaMalloc det");
+            l.dec_ws_bytes = sfa_decode_workspace_bytes(pl->chunk, C, h, w, K);
+            chk(cudaMalloc(&l.d_dec_ws, l.dec_ws_bytes), "cudaMalloc decode ws");
+            if (ok && sfa_decode_workspace_init(l.d_dec_ws, l.dec_ws_bytes, l.stream) != SFA_OK) ok = false;
         }
         if (ok) chk(cudaStreamSynchronize(l.stream), "sync");
     }
@@ -265,7 +270,7 @@ extern "C" int sfa_pipeline_decode_host(SfaPipeline* pl, const float* hm, const 
         SFA_CUDA_TRY(up(d_z, z_coor, 1));
         SFA_CUDA_TRY(up(d_dim, dim, 3));
         if (int rc = sfa_decode(d_hm, cen_offset ? d_off : nullptr, d_dir, d_z, d_dim, nf, C, pl->h, pl->w, K, l.d_det,
-                                nullptr, l.stream))
+                                nullptr, l.d_dec_ws, l.dec_ws_bytes, l.stream))
             return rc;
         SFA_CUDA_TRY(cudaMemcpyAsync(det_host + (size_t)f0 * K * 10, l.d_det, (size_t)nf * K * 10 * sizeof(float),
                                      cudaMemcpyDeviceToHost, l.stream));

@@ -7,42 +7,43 @@
 //   decode :77-105  assembly of [B, K, 10]
 //   post_processing :112-163 ("evaluation_utils copy.py":112-143 per-sample semantics), dense form
 //
-// One kernel, one thread-block CLUSTER of S (<= 8) CTAs per frame:
-//   - each CTA owns a slab of rows of all C classes: it stages slab + halo rows in shared memory
-//     with 16-B coalesced loads, applies the 3x3 peak-keep there and stores every value as an
-//     orderable 32-bit key in a second shared array;
-//   - exact top-K of the slab by an 8-bit MSB-first radix select over those keys (4 passes; the
-//     histogram updates peel the warp's two most common bins first, so the huge tie groups a
-//     heat map has after NMS — suppressed cells are all 0, clamped sigmoids plateau at 1e-4 — cost
-//     one shared atomic per warp instead of 32 serialised ones); ties at the K-th value resolve
-//     toward the lower index;
-//   - the slab's K survivors are ordered locally (rank by counting) and sent to the cluster
-//     leader's shared memory through DSMEM as 64-bit (key << 32 | ~linear_index) words; the leader
-//     merges the S sorted lists (own position + one binary search per other list) and gathers the
-//     8 regression values per detection straight from the NCHW heads (one 32-B sector each — no
-//     NHWC transpose).
-// The heat map is read from HBM exactly once; nothing intermediate is written to HBM.
+// Two kernels per batch, nothing but the candidate list in between (it lives in L2):
+//
+//   peak_candidates : one CTA per (frame, slab of 8 rows, all classes).  Stages slab + halo rows in
+//     shared memory as ORDERABLE 32-bit keys (16-B coalesced loads), applies the 3x3 peak-keep in the
+//     key domain with one thread walking one (class, x) column (3 shared loads per cell), and
+//     appends every cell whose kept value is > 0 to the frame's candidate list as a 64-bit word
+//     (key << 32 | ~linear_index): one block-wide scan and ONE global atomicAdd per CTA.  In any
+//     frame with at least K positive peaks these are the only cells that can reach the top K.
+//   peak_select : one CTA per frame.  Exact top-K of the candidate list by MSB-first radix select
+//     on the score key (4 passes of 8 bits) and, only if equal scores straddle the K-th place, 4 more
+//     passes on the index word — so ties resolve toward the lower (class, y, x), a strict total
+//     order.  The K survivors are ranked by counting and each detection gathers its 8 regression
+//     values straight from the NCHW heads (one 32-B sector each — no NHWC transpose).
+//     Lists that fit (<= 12288 entries) are selected in shared memory, longer ones (clamped
+//     sigmoids plateau at 1e-4 and every plateau cell is a peak) from L2.  A frame with fewer than
+//     K positive cells (tiny maps, all-negative inputs) takes a slow exact path that re-derives the
+//     kept value of every cell from the heat map.
+// The heat map is read from HBM exactly once; nothing but the candidate words is written.
 //
 // Tie rule (torch.topk leaves it implementation-defined): equal scores are ordered by lower class,
 // then lower y*w+x — i.e. descending 64-bit composite key, which is a strict total order.
 #include "sfa_common.cuh"
 
-#include <cooperative_groups.h>
 #include <stdlib.h>
-
-namespace cg = cooperative_groups;
 
 namespace sfa {
 namespace {
 
-constexpr int kMaxSlabs = 8;       // CTAs per cluster (portable maximum)
-constexpr int kThreads = 512;
-constexpr int kWarps = kThreads / 32;
+constexpr int kCandThreads = 512;
+constexpr int kCandWarps = kCandThreads / 32;
+constexpr int kCandRows = 16;              // rows of a slab
+constexpr int kSelThreads = 1024;
+constexpr int kSelSmemItems = 12288;       // candidate words selected from shared memory (96 KB)
 constexpr int kMaxK = 128;
-constexpr int kListCap = 3072;             // compact list of positive cells per slab (u16 entries)
 constexpr uint32_t kNanKey = 0xFFFFFFFFu;  // torch.topk ranks NaN above everything
-constexpr size_t kSmemTarget = 80 * 1024;  // two CTAs per SM with room to spare
-constexpr size_t kSmemLimit = 200 * 1024;
+constexpr uint32_t kZeroKey = 0x80000000u, kPosInfKey = 0xFF800000u, kNegInfKey = 0x007FFFFFu;
+constexpr size_t kDecodeHeaderBytes = 256;
 
 struct DecodeArgs {
     const float* hm;      // [B,C,h,w]
@@ -51,18 +52,143 @@ struct DecodeArgs {
     const float* zc;      // [B,1,h,w]
     const float* dim;     // [B,3,h,w]
     int B, C, h, w, K;
-    int slabs, rows_per_slab;
     int do_nms;
     int vec4;             // hm is 16-B aligned and w % 4 == 0
+    uint32_t* counts;               // [B] candidates per frame (workspace; zero between calls)
+    unsigned long long* cands;      // [B][C*h*w] candidate words (workspace)
     float* det;           // [B,K,10] or null
     int64_t* inds;        // [B,K] or null
     // _topk outputs (all null for decode)
     float* tk_score; int32_t* tk_cls; float* tk_ys; float* tk_xs;
 };
 
-__device__ __forceinline__ float nanmax(float a, float b) {
-    // max_pool2d propagates NaN (ATen: `val > max || isnan(val)`)
-    return (a != a) ? a : ((b != b) ? b : fmaxf(a, b));
+// heat * (maxpool3x3(heat) == heat) in the key domain (evaluation_utils.py:21-26):
+//   own is NaN            -> NaN          (NaN * keep)
+//   max of the 3x3 == own -> own          (keep = 1)
+//   otherwise             -> own * 0 = 0, or NaN when own is +-inf
+__device__ __forceinline__ uint32_t kept_key(uint32_t own, uint32_t m, bool do_nms) {
+    if (!do_nms || own == kNanKey || m == own) return own;
+    return (own == kPosInfKey || own == kNegInfKey) ? kNanKey : kZeroKey;
+}
+
+__global__ void __launch_bounds__(kCandThreads)
+peak_candidates_kernel(DecodeArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned int warp_sums[kCandWarps];
+    __shared__ unsigned int list_base;
+    uint32_t* tkeys = reinterpret_cast<uint32_t*>(smem_raw);   // [C][kCandRows + 2][w]
+    const int b = blockIdx.y;
+    const int C = a.C, h = a.h, w = a.w;
+    const int hw = h * w;
+    const int r0 = blockIdx.x * kCandRows;
+    const int rows = min(kCandRows, h - r0);
+    constexpr int trows = kCandRows + 2;
+    const int tplane = trows * w;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- stage slab + halo rows (r0-1 .. r0+rows) as orderable keys ---------------------------------
+    // Per class the tile rows that exist in the map are one contiguous run of the NCHW plane, so the
+    // copy is linear; rows outside the map get key 0, below every real value (max_pool2d pads with
+    // -inf, whose key is 0x007FFFFF).  NaN maps to the largest key, so an integer max propagates it
+    // exactly like ATen's max_pool2d does.
+    {
+        const float* hmb = a.hm + (size_t)b * C * hw;
+        const int y_lo = r0 - 1;
+        const int tr_first = y_lo < 0 ? 1 : 0;          // first tile row inside the map
+        const int tr_end = min(rows + 2, h - y_lo);     // one past the last tile row inside the map
+        if (a.vec4) {
+            const int w4 = w >> 2, tplane4 = trows * w4;
+            const int lo4 = tr_first * w4, hi4 = tr_end * w4;
+            const int hw4 = hw >> 2;
+            const float4* src0 = reinterpret_cast<const float4*>(hmb) + (ptrdiff_t)y_lo * w4;
+            uint4* dst = reinterpret_cast<uint4*>(tkeys);
+            for (int i = tid; i < C * tplane4; i += kCandThreads) {   // all classes in one flat loop
+                const int c = i / tplane4;
+                const int t4 = i - c * tplane4;
+                uint4 k = make_uint4(0u, 0u, 0u, 0u);
+                if (t4 >= lo4 && t4 < hi4) {
+                    const float4 v = __ldg(src0 + (size_t)c * hw4 + t4);
+                    k = make_uint4(orderable_u32(v.x, kNanKey), orderable_u32(v.y, kNanKey),
+                                   orderable_u32(v.z, kNanKey), orderable_u32(v.w, kNanKey));
+                }
+                dst[i] = k;
+            }
+        } else {
+            const int lo = tr_first * w, hi = tr_end * w;
+            for (int c = 0; c < C; ++c) {
+                const float* src = hmb + (size_t)c * hw + (ptrdiff_t)y_lo * w;
+                uint32_t* dst = tkeys + (size_t)c * tplane;
+                for (int i = tid; i < tplane; i += kCandThreads)
+                    dst[i] = (i >= lo && i < hi) ? orderable_u32(__ldg(src + i), kNanKey) : 0u;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- one thread walks one (class, x) column down the slab ---------------------------------------
+    const size_t frame_cap = (size_t)C * hw;
+    unsigned long long* list = a.cands + (size_t)b * frame_cap;
+    const int ncols = C * w;
+    for (int col0 = 0; col0 < ncols; col0 += kCandThreads) {   // block-uniform trip count (barriers inside)
+        const int col = col0 + tid;
+        const bool valid = col < ncols;
+        const int c = valid ? col / w : 0;
+        const int x = valid ? col - c * w : 0;
+        uint32_t kept[kCandRows];
+        unsigned posmask = 0;
+        if (valid) {
+            const uint32_t* t = tkeys + (size_t)c * tplane + x;   // tile row 0 (halo above the slab)
+            const bool has_l = x > 0, has_r = x < w - 1;
+            uint32_t own = t[w];
+            uint32_t h_prev = t[0], h_cur = own;
+            if (has_l) { h_prev = max(h_prev, t[-1]); h_cur = max(h_cur, t[w - 1]); }
+            if (has_r) { h_prev = max(h_prev, t[1]); h_cur = max(h_cur, t[w + 1]); }
+#pragma unroll
+            for (int r = 0; r < kCandRows; ++r) {
+                kept[r] = 0;
+                if (r < rows) {
+                    const uint32_t* nx = t + (r + 2) * w;
+                    const uint32_t own_next = nx[0];
+                    uint32_t h_next = own_next;
+                    if (has_l) h_next = max(h_next, nx[-1]);
+                    if (has_r) h_next = max(h_next, nx[1]);
+                    kept[r] = kept_key(own, max(max(h_prev, h_cur), h_next), a.do_nms != 0);
+                    if (kept[r] > kZeroKey) posmask |= 1u << r;
+                    h_prev = h_cur; h_cur = h_next; own = own_next;
+                }
+            }
+        }
+        // exclusive scan of the per-thread counts; one global atomicAdd reserves the CTA's run
+        const unsigned cnt = (unsigned)__popc(posmask);
+        unsigned incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned ws = lane < kCandWarps ? warp_sums[lane] : 0u, wi = ws;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned v = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+                if (lane >= d) wi += v;
+            }
+            if (lane < kCandWarps) warp_sums[lane] = wi - ws;   // exclusive warp offsets
+            if (lane == kCandWarps - 1) list_base = wi ? atomicAdd(a.counts + b, wi) : 0u;
+        }
+        __syncthreads();
+        size_t at = (size_t)list_base + warp_sums[warp] + incl - cnt;
+#pragma unroll
+        for (int r = 0; r < kCandRows; ++r) {
+            if (posmask & (1u << r)) {
+                const uint32_t lin = (uint32_t)(c * hw + (r0 + r) * w + x);
+                list[at++] = ((unsigned long long)kept[r] << 32) | (unsigned long long)(0xFFFFFFFFu - lin);
+            }
+        }
+        __syncthreads();   // warp_sums / list_base are reused by the next column group
+    }
 }
 
 // hist[bin] += 1 for every active lane.  The warp's (up to) two most common bins are added by one
@@ -81,289 +207,151 @@ __device__ __forceinline__ void hist_add(unsigned int* hist, bool active, uint32
     if (remaining & (1u << lane)) atomicAdd(&hist[bin], 1u);
 }
 
-__global__ void __launch_bounds__(kThreads)
-decode_kernel(DecodeArgs a) {
-    cg::cluster_group cluster = cg::this_cluster();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ unsigned long long cand[kMaxSlabs * kMaxK];  // leader: S sorted lists
-    __shared__ unsigned long long surv[kMaxK];              // this slab's survivors, unordered
-    __shared__ unsigned int hist[256];
-    __shared__ unsigned int sel_prefix, sel_need, sel_eqpop, n_surv, eq_running, n_pos;
-    __shared__ unsigned int warp_sums[kWarps];
+struct SelectShared {
+    unsigned int hist[256];
+    unsigned int prefix, need, eqpop;
+};
 
-    const int slab = cluster.block_rank();
-    const int S = a.slabs;
-    const int b = blockIdx.y;
-    const int C = a.C, h = a.h, w = a.w, K = a.K;
-    const int hw = h * w;
-    const int r0 = slab * a.rows_per_slab;
-    const int rows = max(0, min(a.rows_per_slab, h - r0));
-    const int n = C * rows * w;                  // elements this CTA selects from
-    const int trows = a.rows_per_slab + 2;       // tile rows incl. halo
-    const int tplane = trows * w;
-    // shared layout: tkeys [C][trows][w] u32 | okeys [C][rows_per_slab][w] u32 | plist [kListCap] u16
-    uint32_t* tkeys = reinterpret_cast<uint32_t*>(smem_raw);
-    uint32_t* okeys = tkeys + (size_t)C * tplane;
-    unsigned short* plist = reinterpret_cast<unsigned short*>(okeys + (size_t)C * a.rows_per_slab * w);
+// MSB-first radix select (descending) over word(i) of the items i in [0, n) that pass filter(i):
+// on return sh.prefix is the 32-bit value of the need-th largest word, sh.need how many of the words
+// EQUAL to it belong to the top `need`, and sh.eqpop how many words equal it.  All threads call.
+// PEEL: aggregate the warp's most common bins (huge tie groups) instead of one atomic per lane.
+template <bool PEEL, class WordFn>
+__device__ void block_radix_select(WordFn word, int n, unsigned need, SelectShared& sh) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    // every CTA of the cluster must be running before anyone writes into the leader's shared memory
-    cluster.barrier_arrive();
-
-    // ---- stage slab + halo rows (r0-1 .. r0+rows) as ORDERABLE KEYS ---------------------------------
-    // Per class the tile rows that exist in the map are one contiguous run of the NCHW plane, so the
-    // copy is linear; rows outside the map get key 0, below every real value (max_pool2d pads with
-    // -inf, whose key is 0x007FFFFF).  NaN maps to the largest key, so an integer max propagates it
-    // exactly like ATen's max_pool2d does.
-    if (tid == 0) { sel_prefix = 0; sel_need = (unsigned)min(K, n); sel_eqpop = 0; n_surv = 0; eq_running = 0; n_pos = 0; }
-    if (rows > 0) {
-        const float* hmb = a.hm + (size_t)b * C * hw;
-        const int y_lo = r0 - 1;
-        const int tr_first = y_lo < 0 ? 1 : 0;                      // first tile row inside the map
-        const int tr_end = min(rows + 2, h - y_lo);                 // one past the last tile row inside the map
-        if (a.vec4) {
-            const int w4 = w >> 2, tplane4 = trows * w4;
-            const int lo4 = tr_first * w4, hi4 = tr_end * w4;
-            for (int c = 0; c < C; ++c) {
-                const float4* src = reinterpret_cast<const float4*>(hmb + (size_t)c * hw) + (ptrdiff_t)y_lo * w4;
-                uint4* dst = reinterpret_cast<uint4*>(tkeys + (size_t)c * tplane);
-                for (int i = tid; i < tplane4; i += kThreads) {
-                    uint4 k = make_uint4(0u, 0u, 0u, 0u);
-                    if (i >= lo4 && i < hi4) {
-                        const float4 v = __ldg(src + i);
-                        k = make_uint4(orderable_u32(v.x, kNanKey), orderable_u32(v.y, kNanKey),
-                                       orderable_u32(v.z, kNanKey), orderable_u32(v.w, kNanKey));
-                    }
-                    dst[i] = k;
-                }
-            }
-        } else {
-            const int lo = tr_first * w, hi = tr_end * w;
-            for (int c = 0; c < C; ++c) {
-                const float* src = hmb + (size_t)c * hw + (ptrdiff_t)y_lo * w;
-                uint32_t* dst = tkeys + (size_t)c * tplane;
-                for (int i = tid; i < tplane; i += kThreads)
-                    dst[i] = (i >= lo && i < hi) ? orderable_u32(__ldg(src + i), kNanKey) : 0u;
-            }
-        }
-    }
+    if (tid == 0) { sh.prefix = 0; sh.need = need; sh.eqpop = 0; }
     __syncthreads();
-
-    // ---- 3x3 peak keep in the key domain: one thread walks one (class, x) column down the slab ------
-    // heat * (maxpool(heat) == heat), evaluation_utils.py:21-26:
-    //   own is NaN             -> NaN           (NaN * keep)
-    //   max of the 3x3 == own  -> own           (keep = 1)
-    //   otherwise              -> own * 0 = 0, or NaN when own is +-inf
-    // Cells with a value above zero are remembered in a per-thread row bitmask and, after one
-    // block-wide scan of the per-thread counts, written to the compact list `plist`: in the common
-    // case they are the only cells that can reach the top K, and the select runs on that list.
-    {
-        const uint32_t kZero = 0x80000000u, kPosInf = 0xFF800000u, kNegInf = 0x007FFFFFu;
-        const int ncols = C * w;
-        const bool listable = a.rows_per_slab <= 64 && n <= 65535;
-        for (int col0 = 0; col0 < ncols; col0 += kThreads) {   // block-uniform trip count (barriers inside)
-            const int col = col0 + tid;
-            const bool valid = col < ncols && rows > 0;
-            const int c = valid ? col / w : 0;
-            const int x = valid ? col - c * w : 0;
-            const uint32_t* t = tkeys + (size_t)c * tplane + x;   // tile row 0 (halo above the slab)
-            const bool has_l = x > 0, has_r = x < w - 1;
-            unsigned long long posmask = 0ull;
-            if (valid) {
-                uint32_t own = t[w];
-                uint32_t h_prev = t[0], h_cur = own;
-                if (has_l) { h_prev = max(h_prev, t[-1]); h_cur = max(h_cur, t[w - 1]); }
-                if (has_r) { h_prev = max(h_prev, t[1]); h_cur = max(h_cur, t[w + 1]); }
-                uint32_t* orow = okeys + (size_t)c * rows * w + x;
-                for (int r = 0; r < rows; ++r) {
-                    const uint32_t* nx = t + (r + 2) * w;
-                    const uint32_t own_next = nx[0];
-                    uint32_t h_next = own_next;
-                    if (has_l) h_next = max(h_next, nx[-1]);
-                    if (has_r) h_next = max(h_next, nx[1]);
-                    uint32_t out = own;
-                    if (a.do_nms && own != kNanKey) {
-                        const uint32_t m = max(max(h_prev, h_cur), h_next);
-                        if (m != own) out = (own == kPosInf || own == kNegInf) ? kNanKey : kZero;
-                    }
-                    orow[r * w] = out;
-                    if (out > kZero) posmask |= 1ull << (r & 63);
-                    h_prev = h_cur; h_cur = h_next; own = own_next;
-                }
-            }
-            // exclusive scan of the per-thread counts -> list offsets (column-major, then row order)
-            const unsigned cnt = listable ? (unsigned)__popcll(posmask) : 0u;
-            unsigned incl = cnt;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        const uint32_t himask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+        for (int i = tid; i < 256; i += kSelThreads) sh.hist[i] = 0;
+        __syncthreads();
+        const uint32_t prefix = sh.prefix;
+        for (int base = 0; base < n; base += kSelThreads) {
+            const int i = base + tid;
+            bool active = false;
+            uint32_t k = 0;
+            if (i < n) active = word(i, k) && ((k ^ prefix) & himask) == 0;
+            if (PEEL) hist_add(sh.hist, active, (k >> shift) & 255u, lane);
+            else if (active) atomicAdd(&sh.hist[(k >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // lane l owns bins 255-8l .. 248-8l (descending); find the bin holding the need-th word
+            const unsigned want = sh.need;
+            unsigned hloc[8];
+            unsigned s = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { hloc[q] = sh.hist[255 - 8 * lane - q]; s += hloc[q]; }
+            unsigned incl = s;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const unsigned v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                if (lane >= d) incl += v;
+                unsigned t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += t;
             }
-            if (lane == 31) warp_sums[warp] = incl;
-            __syncthreads();
-            unsigned at = n_pos + incl - cnt;
-            for (int q = 0; q < warp; ++q) at += warp_sums[q];
-            unsigned block_total = 0;
-            for (int q = 0; q < kWarps; ++q) block_total += warp_sums[q];
-            while (posmask && listable) {
-                const int r = __ffsll((long long)posmask) - 1;
-                posmask &= posmask - 1;
-                if (at < (unsigned)kListCap) plist[at] = (unsigned short)((c * rows + r) * w + x);
-                ++at;
-            }
-            __syncthreads();
-            if (tid == 0) n_pos = listable ? n_pos + block_total : 0xFFFFFFFFu;
-            __syncthreads();
-        }
-    }
-
-    // The select runs over the compact list of positive cells when it holds at least K of them and
-    // did not overflow (then nothing <= 0 can be in the top K); otherwise over every cell of the slab.
-    const int kk = min(K, n);
-    const bool use_list = n_pos >= (unsigned)kk && n_pos <= (unsigned)kListCap && n <= 65535 && kk > 0;
-    const int n_items = use_list ? (int)n_pos : n;
-    auto item_elem = [&](int i) -> int { return use_list ? (int)plist[i] : i; };
-
-    // ---- radix select: key of the K-th largest element of this slab --------------------------------
-    unsigned int eq_total = 0;
-    if (kk > 0) {
-        for (int pass = 0; pass < 4; ++pass) {
-            const int shift = 24 - 8 * pass;
-            const uint32_t himask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
-            for (int i = tid; i < 256; i += kThreads) hist[i] = 0;
-            __syncthreads();
-            const uint32_t prefix = sel_prefix;
-            for (int base = 0; base < n_items; base += kThreads) {
-                const int i = base + tid;
-                bool active = false;
-                uint32_t bin = 0;
-                if (i < n_items) {
-                    const uint32_t k = okeys[item_elem(i)];
-                    active = ((k ^ prefix) & himask) == 0;
-                    bin = (k >> shift) & 255u;
-                }
-                if (use_list) {   // positives are spread over many bins: plain shared atomics
-                    if (active) atomicAdd(&hist[bin], 1u);
-                } else {          // whole slab: huge tie groups (zeros, plateaus) -> peel them
-                    hist_add(hist, active, bin, lane);
-                }
-            }
-            __syncthreads();
-            if (warp == 0) {
-                // lane l owns bins 255-8l .. 248-8l (descending); find the bin holding the need-th element
-                const unsigned need = sel_need;
-                unsigned hloc[8];
-                unsigned s = 0;
+            unsigned excl = incl - s;
+            if (excl < want && want <= incl) {
+                unsigned cum = excl;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) { hloc[q] = hist[255 - 8 * lane - q]; s += hloc[q]; }
-                unsigned incl = s;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    unsigned t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                    if (lane >= d) incl += t;
-                }
-                unsigned excl = incl - s;
-                if (excl < need && need <= incl) {
-                    unsigned cum = excl;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        if (cum < need && need <= cum + hloc[q]) {
-                            sel_prefix = prefix | ((uint32_t)(255 - 8 * lane - q) << shift);
-                            sel_need = need - cum;
-                            sel_eqpop = hloc[q];  // population of the chosen bin
-                            break;
-                        }
-                        cum += hloc[q];
+                for (int q = 0; q < 8; ++q) {
+                    if (cum < want && want <= cum + hloc[q]) {
+                        sh.prefix = prefix | ((uint32_t)(255 - 8 * lane - q) << shift);
+                        sh.need = want - cum;
+                        sh.eqpop = hloc[q];
+                        break;
                     }
+                    cum += hloc[q];
                 }
             }
-            __syncthreads();
         }
-        eq_total = sel_eqpop;  // after the last pass: elements equal to the threshold key
+        __syncthreads();
     }
-    const uint32_t thr = sel_prefix;
-    const unsigned need_eq = sel_need;  // how many of the == thr elements belong to the top K
+}
 
-    // ---- collect the slab's K survivors as composite words -----------------------------------------
-    auto composite = [&](uint32_t k, int e) -> unsigned long long {
-        const int c = e / (rows * w);
-        const int rem = e - c * rows * w;
-        const uint32_t lin = (uint32_t)(c * hw + r0 * w + rem);
-        return ((unsigned long long)k << 32) | (unsigned long long)(0xFFFFFFFFu - lin);
-    };
-    if (kk > 0) {
-        const bool take_all_eq = (eq_total == need_eq);
-        for (int i = tid; i < n_items; i += kThreads) {
-            const int e = item_elem(i);
-            const uint32_t k = okeys[e];
-            if (k > thr || (take_all_eq && k == thr)) {
-                const unsigned pos = atomicAdd(&n_surv, 1u);
-                surv[pos] = composite(k, e);
+__global__ void __launch_bounds__(kSelThreads)
+peak_select_kernel(DecodeArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ SelectShared sel;
+    __shared__ unsigned long long surv[kMaxK];
+    __shared__ unsigned int n_surv;
+    unsigned long long* scand = reinterpret_cast<unsigned long long*>(smem_raw);
+    const int b = blockIdx.x;
+    const int C = a.C, h = a.h, w = a.w, K = a.K;
+    const int hw = h * w;
+    const int tid = threadIdx.x;
+    const size_t frame_cap = (size_t)C * hw;
+    const unsigned long long* gcand = a.cands + (size_t)b * frame_cap;
+
+    const unsigned n_list = a.counts[b];
+    if (tid == 0) n_surv = 0;
+    __syncthreads();
+    if (tid == 0) a.counts[b] = 0;   // ready for the next call on this workspace
+
+    // mode 0: list in shared memory, 1: list in L2 / global, 2: every cell of the map (kept value
+    // re-derived from the heat map) — only when fewer than K cells are positive
+    const int mode = n_list < (unsigned)K ? 2 : (n_list <= (unsigned)kSelSmemItems ? 0 : 1);
+    const int n = mode == 2 ? (int)frame_cap : (int)n_list;
+    if (mode == 0)
+        for (int i = tid; i < n; i += kSelThreads) scand[i] = gcand[i];
+    const float* hmb = a.hm + (size_t)b * C * hw;
+    auto item = [&](int i) -> unsigned long long {
+        if (mode == 0) return scand[i];
+        if (mode == 1) return gcand[i];
+        const int c = i / hw;
+        const int sp = i - c * hw;
+        const int y = sp / w;
+        const int x = sp - y * w;
+        const float* p = hmb + (size_t)c * hw + sp;
+        const uint32_t own = orderable_u32(__ldg(p), kNanKey);
+        uint32_t m = own;
+        if (a.do_nms) {
+            for (int dy = -1; dy <= 1; ++dy) {
+                if (y + dy < 0 || y + dy >= h) continue;
+                for (int dx = -1; dx <= 1; ++dx)
+                    if (x + dx >= 0 && x + dx < w) m = max(m, orderable_u32(__ldg(p + dy * w + dx), kNanKey));
             }
         }
-        if (!take_all_eq) {
-            // more elements tie at the threshold than fit: take the need_eq lowest indices, in order
-            for (int base = 0; base < n; base += kThreads) {
-                __syncthreads();
-                const unsigned running = eq_running;
-                if (running >= need_eq) break;
-                const int e = base + tid;
-                const bool eq = (e < n) && (okeys[e] == thr);
-                const unsigned bal = __ballot_sync(0xFFFFFFFFu, eq);
-                if (lane == 0) warp_sums[warp] = __popc(bal);
-                __syncthreads();
-                unsigned before = running;
-                for (int q = 0; q < warp; ++q) before += warp_sums[q];
-                const unsigned rank = before + __popc(bal & ((1u << lane) - 1u));
-                if (eq && rank < need_eq) {
-                    const unsigned pos = atomicAdd(&n_surv, 1u);
-                    surv[pos] = composite(thr, e);
-                }
-                if (tid == 0) {
-                    unsigned tot = 0;
-                    for (int q = 0; q < kWarps; ++q) tot += warp_sums[q];
-                    eq_running = running + tot;
-                }
-            }
+        return ((unsigned long long)kept_key(own, m, a.do_nms != 0) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
+    };
+    __syncthreads();
+
+    // K-th largest composite word: select on the score key, then (only when equal scores straddle
+    // the K-th place) on the index word among the cells with exactly that score.  A list that fits
+    // shared memory holds positive peaks whose scores are spread over many bins: plain shared
+    // atomics; the long lists / whole maps are dominated by a few values: peel them.
+    auto hi_word = [&](int i, uint32_t& k) { k = (uint32_t)(item(i) >> 32); return true; };
+    if (mode == 0) block_radix_select<false>(hi_word, n, (unsigned)K, sel);
+    else           block_radix_select<true>(hi_word, n, (unsigned)K, sel);
+    const uint32_t thr_hi = sel.prefix;
+    uint32_t thr_lo = 0;
+    const bool straddle = sel.eqpop > sel.need;
+    const unsigned need_eq = sel.need;
+    __syncthreads();
+    if (straddle) {
+        auto lo_word = [&](int i, uint32_t& k) {
+            const unsigned long long v = item(i);
+            k = (uint32_t)v;
+            return (uint32_t)(v >> 32) == thr_hi;
+        };
+        block_radix_select<false>(lo_word, n, need_eq, sel);   // index words are distinct
+        thr_lo = sel.prefix;
+        __syncthreads();
+    }
+    const unsigned long long thr = ((unsigned long long)thr_hi << 32) | thr_lo;
+    for (int i = tid; i < n; i += kSelThreads) {
+        const unsigned long long v = item(i);
+        if (v >= thr) {
+            const unsigned pos = atomicAdd(&n_surv, 1u);
+            if (pos < (unsigned)kMaxK) surv[pos] = v;
         }
     }
     __syncthreads();
 
-    // ---- order the survivors (rank by counting; composites are distinct) and ship them to the leader
-    cluster.barrier_wait();  // pairs with the arrive at the top: all CTAs of the cluster are alive
-    unsigned long long* lead = cluster.map_shared_rank(cand, 0) + slab * kMaxK;
-    for (int i = tid; i < K; i += kThreads) {
-        if (i < kk) {
-            const unsigned long long v = surv[i];
-            int rank = 0;
-            for (int j = 0; j < kk; ++j) rank += (surv[j] > v) ? 1 : 0;
-            lead[rank] = v;
-        } else {
-            lead[i] = 0ull;  // padding sorts below every real candidate
-        }
-    }
-    cluster.sync();  // DSMEM writes are visible to the leader; non-leaders may now exit
-    if (slab != 0) return;
-
-    // ---- leader: merge S descending lists; rank = position in own list + #greater in every other ---
-    for (int i = tid; i < S * K; i += kThreads) {
-        const int s = i / K;
-        const int j = i - s * K;
-        const unsigned long long v = cand[s * kMaxK + j];
-        if (v == 0ull) continue;
-        int rank = j;
-        for (int t = 0; t < S; ++t) {
-            if (t == s) continue;
-            const unsigned long long* lst = cand + t * kMaxK;
-            int lo = 0, hi = K;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (lst[mid] > v) lo = mid + 1; else hi = mid;
-            }
-            rank += lo;
-        }
-        if (rank >= K) continue;
-        const int k = rank;
+    // ---- rank the K survivors (composites are distinct) and emit the detections ---------------------
+    for (int i = tid; i < K; i += kSelThreads) {
+        const unsigned long long v = surv[i];
+        int k = 0;
+        for (int j = 0; j < K; ++j) k += (surv[j] > v) ? 1 : 0;
         const uint32_t key = (uint32_t)(v >> 32);
         const uint32_t lin = 0xFFFFFFFFu - (uint32_t)v;
         const int c = lin / hw;
@@ -399,6 +387,11 @@ decode_kernel(DecodeArgs a) {
             d[9] = (float)c;
         }
     }
+}
+
+__device__ __forceinline__ float nanmax(float a, float b) {
+    // max_pool2d propagates NaN (ATen: `val > max || isnan(val)`)
+    return (a != a) ? a : ((b != b) ? b : fmaxf(a, b));
 }
 
 __global__ void __launch_bounds__(256)
@@ -445,54 +438,43 @@ post_process_kernel(const float* __restrict__ det, int n, int num_classes, float
     keep[i] = (c >= 0 && score > thresh) ? 1 : 0;            // :134, :152
 }
 
-size_t slab_smem_bytes(int C, int h, int w, int slabs) {
-    const int rps = (h + slabs - 1) / slabs;
-    return (size_t)C * (rps + 2) * w * sizeof(float) + (size_t)C * rps * w * sizeof(uint32_t) +
-           (size_t)kListCap * sizeof(unsigned short);
+size_t decode_workspace_bytes(int B, int C, int h, int w) {
+    return kDecodeHeaderBytes + (((size_t)(B > 0 ? B : 1) * sizeof(uint32_t) + 255) / 256) * 256 +
+           (size_t)(B > 0 ? B : 1) * C * h * w * sizeof(unsigned long long);
 }
 
-int launch_decode(DecodeArgs a, cudaStream_t stream) {
+int launch_decode(DecodeArgs a, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     SFA_REQUIRE(a.B >= 0 && a.C > 0 && a.h > 0 && a.w > 0, "bad head shape B=%d C=%d h=%d w=%d", a.B, a.C, a.h, a.w);
     SFA_REQUIRE(a.K > 0 && a.K <= kMaxK, "K=%d unsupported (1..%d)", a.K, kMaxK);
     // torch.topk(scores.view(B, C, -1), K) raises when K > h*w (evaluation_utils.py:50)
     SFA_REQUIRE((long long)a.K <= (long long)a.h * a.w, "K=%d exceeds h*w=%d (the reference's topk raises)", a.K, a.h * a.w);
     SFA_REQUIRE((long long)a.C * a.h * a.w < 0x7FFFFFFFll, "head too large");
     if (a.B == 0) return SFA_OK;
-    // slabs per frame: as few as keep a CTA's tile + keys within ~74 KB (3 CTAs / SM), more when the
-    // batch alone cannot fill the 148 SMs; at most the portable cluster size
-    int slabs = 1;
-    while (slabs < kMaxSlabs && slabs < a.h &&
-           (slab_smem_bytes(a.C, a.h, a.w, slabs) > kSmemTarget || (long long)a.B * slabs < 2 * kNumSMs))
-        ++slabs;
-    if (const char* e = getenv("SFA_DECODE_SLABS")) {   // tuning aid
-        int v = atoi(e);
-        if (v >= 1 && v <= kMaxSlabs && v <= a.h) slabs = v;
+    SFA_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+                "workspace must be a 256-B aligned device pointer");
+    const size_t need = decode_workspace_bytes(a.B, a.C, a.h, a.w);
+    if (workspace_bytes < need) {
+        set_error("workspace too small: %zu < %zu (size it with sfa_decode_workspace_bytes)", workspace_bytes, need);
+        return SFA_ERR_WORKSPACE_TOO_SMALL;
     }
-    a.slabs = slabs;
-    a.rows_per_slab = (a.h + slabs - 1) / slabs;
-    const size_t smem = slab_smem_bytes(a.C, a.h, a.w, slabs);
-    if (smem > kSmemLimit) {
-        set_error("head %dx%dx%d too large for the fused decode (%zu B of shared memory per slab)", a.C, a.h, a.w, smem);
+    const size_t tile_smem = (size_t)a.C * (kCandRows + 2) * a.w * sizeof(uint32_t);
+    if (tile_smem > 200 * 1024) {
+        set_error("head rows of %d x %d values do not fit the peak-keep tile (%zu B of shared memory)", a.C, a.w, tile_smem);
         return SFA_ERR_UNSUPPORTED;
     }
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    a.counts = reinterpret_cast<uint32_t*>(ws + kDecodeHeaderBytes);
+    a.cands = reinterpret_cast<unsigned long long*>(ws + kDecodeHeaderBytes + (((size_t)a.B * sizeof(uint32_t) + 255) / 256) * 256);
     a.vec4 = ((a.w & 3) == 0 && (reinterpret_cast<uintptr_t>(a.hm) & 15) == 0) ? 1 : 0;
 
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(slabs, a.B, 1);
-    cfg.blockDim = dim3(kThreads, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = slabs;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    SFA_CUDA_TRY(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-    cudaError_t err = cudaSuccess;
-    SFA_LAUNCH("peak_decode", stream, err = cudaLaunchKernelEx(&cfg, decode_kernel, a));
-    SFA_CUDA_TRY(err);
+    if (tile_smem > 48 * 1024)
+        SFA_CUDA_TRY(cudaFuncSetAttribute(peak_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+    dim3 cgrid((a.h + kCandRows - 1) / kCandRows, a.B);
+    SFA_LAUNCH("peak_candidates", stream, peak_candidates_kernel<<<cgrid, kCandThreads, tile_smem, stream>>>(a));
+    const size_t sel_smem = (size_t)kSelSmemItems * sizeof(unsigned long long);
+    SFA_CUDA_TRY(cudaFuncSetAttribute(peak_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+    SFA_LAUNCH("peak_select", stream, peak_select_kernel<<<a.B, kSelThreads, sel_smem, stream>>>(a));
+    SFA_CUDA_TRY(cudaGetLastError());
     return SFA_OK;
 }
 
@@ -501,27 +483,44 @@ int launch_decode(DecodeArgs a, cudaStream_t stream) {
 
 using namespace sfa;
 
+extern "C" size_t sfa_decode_workspace_bytes(int32_t B, int32_t C, int32_t h, int32_t w, int32_t K) {
+    (void)K;
+    if (B < 0 || C <= 0 || h <= 0 || w <= 0) {
+        set_error("bad head shape B=%d C=%d h=%d w=%d", B, C, h, w);
+        return 0;
+    }
+    return decode_workspace_bytes(B, C, h, w);
+}
+
+extern "C" int sfa_decode_workspace_init(void* workspace, size_t workspace_bytes, sfa_stream_t stream) {
+    SFA_REQUIRE(workspace != nullptr || workspace_bytes == 0, "workspace is NULL");
+    // only the per-frame candidate counters have to start at zero; clearing everything is simplest
+    if (workspace_bytes) SFA_CUDA_TRY(cudaMemsetAsync(workspace, 0, workspace_bytes, (cudaStream_t)stream));
+    return SFA_OK;
+}
+
 extern "C" int sfa_decode(const float* hm, const float* cen_offset, const float* direction, const float* z_coor,
                           const float* dim, int32_t B, int32_t C, int32_t h, int32_t w, int32_t K, float* det,
-                          int64_t* inds, sfa_stream_t stream) {
+                          int64_t* inds, void* workspace, size_t workspace_bytes, sfa_stream_t stream) {
     SFA_REQUIRE(B == 0 || (hm && direction && z_coor && dim && det), "NULL pointer argument");
     DecodeArgs a = {};
     a.hm = hm; a.off = cen_offset; a.dir = direction; a.zc = z_coor; a.dim = dim;
     a.B = B; a.C = C; a.h = h; a.w = w; a.K = K;
     a.do_nms = 1;
     a.det = det; a.inds = inds;
-    return launch_decode(a, (cudaStream_t)stream);
+    return launch_decode(a, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int sfa_topk(const float* scores, int32_t B, int32_t C, int32_t h, int32_t w, int32_t K, float* score,
-                        int64_t* inds, int32_t* clses, float* ys, float* xs, sfa_stream_t stream) {
+                        int64_t* inds, int32_t* clses, float* ys, float* xs, void* workspace, size_t workspace_bytes,
+                        sfa_stream_t stream) {
     SFA_REQUIRE(B == 0 || (scores && score && inds && clses && ys && xs), "NULL pointer argument");
     DecodeArgs a = {};
     a.hm = scores;
     a.B = B; a.C = C; a.h = h; a.w = w; a.K = K;
     a.do_nms = 0;
     a.inds = inds; a.tk_score = score; a.tk_cls = clses; a.tk_ys = ys; a.tk_xs = xs;
-    return launch_decode(a, (cudaStream_t)stream);
+    return launch_decode(a, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int sfa_nms(const float* heat, int32_t planes, int32_t h, int32_t w, float* out, sfa_stream_t stream) {

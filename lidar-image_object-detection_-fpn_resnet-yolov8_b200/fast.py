@@ -108,6 +108,30 @@ def filter_lidar_device(points, geom: BevGeometry):
     return out[: int(count.item())]
 
 
+_decode_workspaces = {}
+
+
+def decode_workspace(device, B, C, h, w, K):
+    """(pointer, bytes) of a cached, initialised sfa_decode workspace for up to B frames of [C,h,w]
+    heads on `device` (one per device and head shape, grown on demand)."""
+    lib = _lib.load()
+    device = torch.device(device)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), C, h, w)
+    ent = _decode_workspaces.get(key)
+    if ent is None or ent[2] < B:
+        cap = max(B, 2 * ent[2] if ent else B)
+        nbytes = lib.sfa_decode_workspace_bytes(cap, C, h, w, K)
+        if nbytes == 0:
+            raise _lib.SfaError(-1, _lib.last_error())
+        with torch.cuda.device(device):
+            buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+            ptr = buf.data_ptr() + (-buf.data_ptr()) % 256
+            _lib.check(lib.sfa_decode_workspace_init(ctypes.c_void_p(ptr), nbytes, _stream_ptr(device)))
+        ent = (buf, ptr, cap, nbytes)
+        _decode_workspaces[key] = ent
+    return ent[1], ent[3]
+
+
 def decode_device(hm_cen, cen_offset, direction, z_coor, dim, K=40, out=None, inds=None):
     """decode (utils/evaluation_utils.py:77-105) on CUDA float32 NCHW-contiguous heads, writing into
     `out` [B,K,10] (allocated when None) — no allocation, copy or sync when `out` is given, so the
@@ -125,9 +149,10 @@ def decode_device(hm_cen, cen_offset, direction, z_coor, dim, K=40, out=None, in
         out = torch.empty((B, K, 10), dtype=torch.float32, device=hm_cen.device)
     elif out.shape != (B, K, 10) or out.dtype != torch.float32 or not out.is_contiguous():
         raise ValueError("out must be contiguous float32 [B,K,10]")
+    ws_ptr, ws_bytes = decode_workspace(hm_cen.device, B, C, h, w, K)
     with torch.cuda.device(hm_cen.device):
         rc = lib.sfa_decode(_ptr(hm_cen), _ptr(cen_offset), _ptr(direction), _ptr(z_coor), _ptr(dim), B, C, h, w, K,
-                            _ptr(out), _ptr(inds), _stream_ptr(hm_cen.device))
+                            _ptr(out), _ptr(inds), ctypes.c_void_p(ws_ptr), ws_bytes, _stream_ptr(hm_cen.device))
     if rc != 0:
         # torch.topk raises RuntimeError when K > h*w (evaluation_utils.py:50): same exception type
         raise RuntimeError("decode: " + _lib.last_error())

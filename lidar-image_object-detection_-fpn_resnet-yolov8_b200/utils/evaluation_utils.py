@@ -73,8 +73,11 @@ def _topk(scores, K=40):
     clses = torch.empty((B, K), dtype=torch.int32, device=dev)
     ys = torch.empty((B, K), dtype=torch.float32, device=dev)
     xs = torch.empty((B, K), dtype=torch.float32, device=dev)
+    from ..fast import decode_workspace
+    ws_ptr, ws_bytes = decode_workspace(dev, B, C, h, w, K)
     with torch.cuda.device(dev):
-        _raise_like_topk(lib.sfa_topk(_p(x), B, C, h, w, K, _p(score), _p(inds), _p(clses), _p(ys), _p(xs), _stream(x)))
+        _raise_like_topk(lib.sfa_topk(_p(x), B, C, h, w, K, _p(score), _p(inds), _p(clses), _p(ys), _p(xs),
+                                      ctypes.c_void_p(ws_ptr), ws_bytes, _stream(x)))
     res = (score, inds, clses, ys, xs)
     return tuple(t.cpu() for t in res) if was_cpu else res
 
