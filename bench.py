@@ -46,11 +46,12 @@ BYTES_DECODE = 4 * HEAD_C * HEAD_H * HEAD_W + 32 * 8 * TOPK + 40 * TOPK
 BYTES_FRAME = BYTES_BEV + BYTES_DECODE
 # algorithmic bytes per FRAME each kernel is responsible for (DESIGN.md "kernels")
 KERNEL_BYTES = {
-    "bev_raster": 16 * N_POINTS,
-    "bev_finalize": 12 * BEV_H * BEV_W,
-    "bev_bin": 16 * N_POINTS,
-    "bev_band": 12 * BEV_H * BEV_W,
-    "peak_decode": BYTES_DECODE,
+    "bev_raster": 16 * N_POINTS,            # global-atomic path: points in
+    "bev_finalize": 12 * BEV_H * BEV_W,     #                     planes out
+    "bev_bin": 16 * N_POINTS,               # tiled path: points in (records stay in L2)
+    "bev_band": 12 * BEV_H * BEV_W,         #             planes out
+    "peak_candidates": 4 * HEAD_C * HEAD_H * HEAD_W,    # heat map in (candidate list stays in L2)
+    "peak_select": 32 * 8 * TOPK + 40 * TOPK,           # gathered regression sectors + detections out
     "post_process": 40 * TOPK + 32 * TOPK + 5 * TOPK,
 }
 
@@ -283,7 +284,17 @@ def run_b200(args):
     pp_out = (torch.empty((B, TOPK, 8), dtype=torch.float32, device=dev),
               torch.empty((B, TOPK), dtype=torch.int32, device=dev), torch.empty((B, TOPK), dtype=torch.uint8, device=dev))
 
+    def step_serial(s):
+        """Same launches as step(), all on the current stream (per-kernel event timing, ncu)."""
+        pts, heads = dev_sets[s % sets]
+        for i, (b0, b1) in enumerate(lane_frames):
+            rasts[i](pts[b0 * N_POINTS:b1 * N_POINTS], lane_offsets[i], N_POINTS, out=bev_out[b0:b1])
+        fast.decode_device(*heads, K=TOPK, out=det_out)
+        fast.post_process_dense(det_out, out=pp_out)
+
     def step(s):
+        if args.eager:
+            return step_serial(s)
         pts, heads = dev_sets[s % sets]
         main = torch.cuda.current_stream(dev)
         for st in side:
@@ -356,7 +367,7 @@ def run_b200(args):
     torch.cuda.synchronize()
     with lib.profile() as prof:
         for i in range(max(4, sets)):
-            step(i)
+            step_serial(i)
         torch.cuda.synchronize()
     hbm_gbs, peak_src = peaks()
     n_prof_steps = max(4, sets)
@@ -483,7 +494,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--sets", type=int, default=4)
-    ap.add_argument("--lanes", type=int, default=2, help="independent BEV streams the batch is split over")
+    ap.add_argument("--lanes", type=int, default=4, help="independent BEV streams the batch is split over")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true",

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Single-pass ncu collection (no kernel replay, caches untouched) of DRAM bytes per launch for an eager step.
 set -u
-CMD="python bench.py --steps 2 --warmup 3 --eager --no-e2e --no-cpu-baseline"
+CMD="python bench.py --steps 2 --warmup 3 --eager --lanes 1 --no-e2e --no-cpu-baseline"
 mkdir -p gpurun_out
 for RING in ${RINGS:-32 16 8}; do
   SFA_BEV_TILED_RING=$RING ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct \

@@ -5,7 +5,7 @@
 set -u
 PAT="${1:-decode_kernel|bev_band_kernel|bev_bin_kernel}"
 COUNT="${2:-9}"
-CMD="python bench.py --steps 2 --warmup 3 --eager --no-e2e --no-cpu-baseline"
+CMD="python bench.py --steps 2 --warmup 3 --eager --lanes 1 --no-e2e --no-cpu-baseline"
 mkdir -p gpurun_out
 $CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -20 gpurun_out/plain.log; exit 1; }
 if [ "${3:-}" = "list" ]; then

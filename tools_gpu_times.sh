@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu launch list (device time of every launch; single pass, caches untouched) of an eager bench step.
 set -u
-CMD="python bench.py --steps 2 --warmup 3 --eager --no-e2e --no-cpu-baseline"
+CMD="python bench.py --steps 2 --warmup 3 --eager --lanes 1 --no-e2e --no-cpu-baseline"
 mkdir -p gpurun_out
 $CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -20 gpurun_out/plain.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
