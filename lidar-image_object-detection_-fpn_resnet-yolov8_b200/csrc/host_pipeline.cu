@@ -156,7 +156,7 @@ extern "C" SfaPipeline* sfa_pipeline_create(int32_t device, int32_t max_frames, 
     pl->device = device;
     pl->max_frames = max_frames;
     const char* e = getenv("SFA_PIPELINE_CHUNK");
-    int chunk = e ? atoi(e) : 8;
+    int chunk = e ? atoi(e) : 16;
     if (chunk < 1) chunk = 1;
     pl->chunk = max_frames < chunk ? max_frames : chunk;
     pl->max_points = max_points_per_frame;
