@@ -333,7 +333,9 @@ peak_select_kernel(DecodeArgs a) {
             k = (uint32_t)v;
             return (uint32_t)(v >> 32) == thr_hi;
         };
-        block_radix_select<false>(lo_word, n, need_eq, sel);   // index words are distinct
+        // index words are distinct but share their leading bytes (indices are < C*h*w): the first
+        // passes put every tied cell into one bin, so aggregate
+        block_radix_select<true>(lo_word, n, need_eq, sel);
         thr_lo = sel.prefix;
         __syncthreads();
     }
