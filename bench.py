@@ -270,68 +270,102 @@ def run_b200(args):
     dev_sets = []
     for pts, heads in host_sets:
         dev_sets.append((torch.from_numpy(pts).to(dev).reshape(-1, 4), tuple(t.to(dev) for t in heads)))
-    offsets = torch.arange(B + 1, dtype=torch.int64, device=dev) * N_POINTS
-    # The batch is split over `lanes` independent rasterisers, each with its own workspace and CUDA
-    # stream, and the decode runs on a stream of its own: sweeps and heads are independent inputs, so
-    # inside one graph replay the latency-bound phases of one lane overlap the others'.
+    # A step runs on an "engine": the batch is split over `lanes` independent rasterisers, each with
+    # its own workspace and CUDA stream, and the decode runs on a stream of its own — sweeps and heads
+    # are independent inputs, so inside one graph replay the latency-bound phases of one lane overlap
+    # the others'.  `pipelines` engines (each with its own workspaces and output buffers) take the
+    # steps in turn on their own launch streams, so step i+1 ramps up while step i drains — what a
+    # double-buffered inference loop does.  Every step does the full work; nothing is shared or reused.
     lanes = max(1, min(args.lanes, B))
     lane_frames = [(B * i // lanes, B * (i + 1) // lanes) for i in range(lanes)]
-    rasts = [fast.BevRasterizer(geom, max_batch=b1 - b0, max_points=N_POINTS, device=dev) for b0, b1 in lane_frames]
     lane_offsets = [torch.arange(b1 - b0 + 1, dtype=torch.int64, device=dev) * N_POINTS for b0, b1 in lane_frames]
-    side = [torch.cuda.Stream(device=dev) for _ in range(lanes)]   # lanes 1.. and the decode
-    bev_out = torch.empty((B, 3, BEV_H, BEV_W), dtype=torch.float32, device=dev)
-    det_out = torch.empty((B, TOPK, 10), dtype=torch.float32, device=dev)
-    pp_out = (torch.empty((B, TOPK, 8), dtype=torch.float32, device=dev),
-              torch.empty((B, TOPK), dtype=torch.int32, device=dev), torch.empty((B, TOPK), dtype=torch.uint8, device=dev))
 
-    def step_serial(s):
-        """Same launches as step(), all on the current stream (per-kernel event timing, ncu)."""
-        pts, heads = dev_sets[s % sets]
-        for i, (b0, b1) in enumerate(lane_frames):
-            rasts[i](pts[b0 * N_POINTS:b1 * N_POINTS], lane_offsets[i], N_POINTS, out=bev_out[b0:b1])
-        fast.decode_device(*heads, K=TOPK, out=det_out)
-        fast.post_process_dense(det_out, out=pp_out)
+    class Engine:
+        def __init__(self):
+            self.rasts = [fast.BevRasterizer(geom, max_batch=b1 - b0, max_points=N_POINTS, device=dev)
+                          for b0, b1 in lane_frames]
+            self.side = [torch.cuda.Stream(device=dev) for _ in range(lanes)]   # lanes 1.. and the decode
+            self.launch = torch.cuda.Stream(device=dev)
+            self.bev_out = torch.empty((B, 3, BEV_H, BEV_W), dtype=torch.float32, device=dev)
+            self.det_out = torch.empty((B, TOPK, 10), dtype=torch.float32, device=dev)
+            self.pp_out = (torch.empty((B, TOPK, 8), dtype=torch.float32, device=dev),
+                           torch.empty((B, TOPK), dtype=torch.int32, device=dev),
+                           torch.empty((B, TOPK), dtype=torch.uint8, device=dev))
+            self.dec_ws = fast.DecodeWorkspace(dev, B, HEAD_C, HEAD_H, HEAD_W, TOPK)
+            self.graphs = []
 
-    def step(s):
-        if args.eager:
-            return step_serial(s)
-        pts, heads = dev_sets[s % sets]
-        main = torch.cuda.current_stream(dev)
-        for st in side:
-            st.wait_stream(main)
-        for i, (b0, b1) in enumerate(lane_frames):
-            with torch.cuda.stream(main if i == 0 else side[i - 1]):
-                rasts[i](pts[b0 * N_POINTS:b1 * N_POINTS], lane_offsets[i], N_POINTS, out=bev_out[b0:b1])
-        with torch.cuda.stream(side[-1]):
-            fast.decode_device(*heads, K=TOPK, out=det_out)
-            fast.post_process_dense(det_out, out=pp_out)
-        for st in side:
-            main.wait_stream(st)
+        def step_serial(self, s):
+            """Same launches as step(), all on the current stream (per-kernel event timing, ncu)."""
+            pts, heads = dev_sets[s % sets]
+            for i, (b0, b1) in enumerate(lane_frames):
+                self.rasts[i](pts[b0 * N_POINTS:b1 * N_POINTS], lane_offsets[i], N_POINTS, out=self.bev_out[b0:b1])
+            fast.decode_device(*heads, K=TOPK, out=self.det_out, workspace=self.dec_ws)
+            fast.post_process_dense(self.det_out, out=self.pp_out)
 
-    # eager warm-up (also loads every kernel), then one graph per input set
-    for s in range(sets):
-        step(s)
-    torch.cuda.synchronize()
+        def step(self, s):
+            if args.eager:
+                return self.step_serial(s)
+            pts, heads = dev_sets[s % sets]
+            main = torch.cuda.current_stream(dev)
+            for st in self.side:
+                st.wait_stream(main)
+            for i, (b0, b1) in enumerate(lane_frames):
+                with torch.cuda.stream(main if i == 0 else self.side[i - 1]):
+                    self.rasts[i](pts[b0 * N_POINTS:b1 * N_POINTS], lane_offsets[i], N_POINTS, out=self.bev_out[b0:b1])
+            with torch.cuda.stream(self.side[-1]):
+                fast.decode_device(*heads, K=TOPK, out=self.det_out, workspace=self.dec_ws)
+                fast.post_process_dense(self.det_out, out=self.pp_out)
+            for st in self.side:
+                main.wait_stream(st)
+
     class _Eager:
-        def __init__(self, s):
-            self.s = s
+        def __init__(self, eng, s):
+            self.eng, self.s = eng, s
 
         def replay(self):
-            step(self.s)
+            self.eng.step(self.s)
 
-    graphs, launches_per_step = [], 0
+    n_pipe = 1 if args.eager else max(1, args.pipelines)
+    engines = [Engine() for _ in range(n_pipe)]
+    launches_per_step = 0
     cap_stream = torch.cuda.Stream(device=dev)
-    for s in range(sets):
-        n0 = lib.kernel_launches()
-        if args.eager:
-            g = _Eager(s)
-            g.replay()
+    for eng in engines:
+        for s in range(sets):   # eager warm-up (also loads every kernel)
+            eng.step(s)
+        torch.cuda.synchronize()
+        for s in range(sets):   # then one graph per input set
+            n0 = lib.kernel_launches()
+            if args.eager:
+                g = _Eager(eng, s)
+                g.replay()
+            else:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=cap_stream):
+                    eng.step(s)
+            launches_per_step = lib.kernel_launches() - n0
+            eng.graphs.append(g)
+    step_serial = engines[0].step_serial
+
+    def replay(i):
+        """Step i: engine i % n_pipe on its own launch stream (steps of one engine stay in order)."""
+        eng = engines[i % n_pipe]
+        if n_pipe == 1:
+            eng.graphs[i % sets].replay()
         else:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=cap_stream):
-                step(s)
-        launches_per_step = lib.kernel_launches() - n0
-        graphs.append(g)
+            with torch.cuda.stream(eng.launch):
+                eng.graphs[i % sets].replay()
+
+    def fork():
+        main = torch.cuda.current_stream(dev)
+        if n_pipe > 1:
+            for eng in engines:
+                eng.launch.wait_stream(main)
+
+    def join():
+        main = torch.cuda.current_stream(dev)
+        if n_pipe > 1:
+            for eng in engines:
+                main.wait_stream(eng.launch)
 
     def barrier():
         if world > 1:
@@ -342,16 +376,20 @@ def run_b200(args):
     with ClockSampler(local_rank) as clocks:
         # warm-up: at least W (>= 3) steps and at least 0.5 s, so clocks settle and get sampled under load
         n_warm, t_w = 0, time.monotonic()
+        fork()
         while n_warm < max(args.warmup, 3) or (not args.eager and time.monotonic() - t_w < 0.5):
-            graphs[n_warm % sets].replay()
+            replay(n_warm)
             n_warm += 1
             if n_warm % 16 == 0:
                 torch.cuda.synchronize()
+        join()
         barrier()
         t_begin = time.monotonic()
         e0.record()
+        fork()
         for i in range(args.steps):
-            graphs[i % sets].replay()
+            replay(i)
+        join()
         e1.record()
         barrier()
         t_end = time.monotonic()
@@ -460,7 +498,7 @@ def run_b200(args):
                                    % (B, N_POINTS, B, TOPK, HEAD_C, HEAD_H, HEAD_W),
                        "frames_per_step_per_gpu": B, "l2_policy": "inputs rotate over %d distinct batches (%.0f MB) > L2" %
                        (sets, sets * B * (16 * N_POINTS + 44 * HEAD_H * HEAD_W) / 1e6),
-                       "cuda_graph": not args.eager, "streams": "%d BEV lanes + 1 decode stream per GPU" % lanes, "sharding": "frames, no collective on the data path"},
+                       "cuda_graph": not args.eager, "streams": "%d engine(s) alternating steps; per engine %d BEV lanes + 1 decode stream" % (n_pipe, lanes), "sharding": "frames, no collective on the data path"},
             "gpu_launches": int(launches_per_step * args.steps),
             "e2e": e2e, "roofline": roofline, "roofline_path": roofline_path, "kernels": kern,
             "cpu_baseline": cpu_baseline, "clocks": clocks.summary(t_begin, t_end),
@@ -509,6 +547,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--sets", type=int, default=4)
+    ap.add_argument("--pipelines", type=int, default=2,
+                    help="engines (own workspaces, outputs, streams) that take the steps in turn, so consecutive steps overlap")
     ap.add_argument("--lanes", type=int, default=4, help="independent BEV streams the batch is split over")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -132,7 +132,24 @@ def decode_workspace(device, B, C, h, w, K):
     return ent[1], ent[3]
 
 
-def decode_device(hm_cen, cen_offset, direction, z_coor, dim, K=40, out=None, inds=None):
+class DecodeWorkspace:
+    """An explicit sfa_decode workspace for up to B frames of [C,h,w] heads.  decode_device uses a
+    cached per-(device, shape) workspace by default; calls that may run CONCURRENTLY (different
+    streams) must each bring their own."""
+
+    def __init__(self, device, B, C, h, w, K):
+        lib = _lib.load()
+        self.device, self.shape, self.frames = torch.device(device), (C, h, w), int(B)
+        self.nbytes = lib.sfa_decode_workspace_bytes(self.frames, C, h, w, K)
+        if self.nbytes == 0:
+            raise _lib.SfaError(-1, _lib.last_error())
+        with torch.cuda.device(self.device):
+            self.buf = torch.empty(self.nbytes + 256, dtype=torch.uint8, device=self.device)
+            self.ptr = self.buf.data_ptr() + (-self.buf.data_ptr()) % 256
+            _lib.check(lib.sfa_decode_workspace_init(ctypes.c_void_p(self.ptr), self.nbytes, _stream_ptr(self.device)))
+
+
+def decode_device(hm_cen, cen_offset, direction, z_coor, dim, K=40, out=None, inds=None, workspace=None):
     """decode (utils/evaluation_utils.py:77-105) on CUDA float32 NCHW-contiguous heads, writing into
     `out` [B,K,10] (allocated when None) — no allocation, copy or sync when `out` is given, so the
     call can be captured in a CUDA graph.  `inds` optional int64 [B,K] receives the spatial indices."""
@@ -149,7 +166,12 @@ def decode_device(hm_cen, cen_offset, direction, z_coor, dim, K=40, out=None, in
         out = torch.empty((B, K, 10), dtype=torch.float32, device=hm_cen.device)
     elif out.shape != (B, K, 10) or out.dtype != torch.float32 or not out.is_contiguous():
         raise ValueError("out must be contiguous float32 [B,K,10]")
-    ws_ptr, ws_bytes = decode_workspace(hm_cen.device, B, C, h, w, K)
+    if workspace is not None:
+        if workspace.shape != (C, h, w) or workspace.frames < B:
+            raise ValueError("workspace was sized for %d frames of %s heads" % (workspace.frames, workspace.shape))
+        ws_ptr, ws_bytes = workspace.ptr, workspace.nbytes
+    else:
+        ws_ptr, ws_bytes = decode_workspace(hm_cen.device, B, C, h, w, K)
     with torch.cuda.device(hm_cen.device):
         rc = lib.sfa_decode(_ptr(hm_cen), _ptr(cen_offset), _ptr(direction), _ptr(z_coor), _ptr(dim), B, C, h, w, K,
                             _ptr(out), _ptr(inds), ctypes.c_void_p(ws_ptr), ws_bytes, _stream_ptr(hm_cen.device))
