@@ -270,7 +270,7 @@ extern "C" int sfa_pipeline_decode_host(SfaPipeline* pl, const float* hm, const 
         SFA_CUDA_TRY(up(d_z, z_coor, 1));
         SFA_CUDA_TRY(up(d_dim, dim, 3));
         if (int rc = sfa_decode(d_hm, cen_offset ? d_off : nullptr, d_dir, d_z, d_dim, nf, C, pl->h, pl->w, K, l.d_det,
-                                nullptr, l.d_dec_ws, l.dec_ws_bytes, l.stream))
+                                nullptr, 0, l.d_dec_ws, l.dec_ws_bytes, l.stream))
             return rc;
         SFA_CUDA_TRY(cudaMemcpyAsync(det_host + (size_t)f0 * K * 10, l.d_det, (size_t)nf * K * 10 * sizeof(float),
                                      cudaMemcpyDeviceToHost, l.stream));

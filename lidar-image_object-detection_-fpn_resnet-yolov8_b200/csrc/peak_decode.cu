@@ -53,6 +53,7 @@ struct DecodeArgs {
     const float* dim;     // [B,3,h,w]
     int B, C, h, w, K;
     int do_nms;
+    int apply_sigmoid;    // hm and cen_offset are raw logits: apply _sigmoid (utils/torch_utils.py:44-45) on load
     int vec4;             // hm is 16-B aligned and w % 4 == 0
     uint32_t* counts;               // [B] candidates per frame (workspace; zero between calls)
     unsigned long long* cands;      // [B][C*h*w] candidate words (workspace)
@@ -61,6 +62,15 @@ struct DecodeArgs {
     // _topk outputs (all null for decode)
     float* tk_score; int32_t* tk_cls; float* tk_ys; float* tk_xs;
 };
+
+// _sigmoid of utils/torch_utils.py:44-45: clamp(sigmoid(x), 1e-4, 1 - 1e-4).  The clamp bounds are the
+// float32 roundings torch uses; sigmoid itself agrees with torch's to the last ulp or two, which is
+// why the fused path is tolerance-checked while the un-fused one is bit-exact.
+__device__ __forceinline__ float sigmoid_clamped(float x) {
+    const float s = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+    return fminf(fmaxf(s, 1e-4f), 1.0f - 1e-4f);
+}
+__device__ __forceinline__ float act(float x, bool apply_sigmoid) { return apply_sigmoid ? sigmoid_clamped(x) : x; }
 
 // heat * (maxpool3x3(heat) == heat) in the key domain (evaluation_utils.py:21-26):
 //   own is NaN            -> NaN          (NaN * keep)
@@ -108,8 +118,9 @@ peak_candidates_kernel(DecodeArgs a) {
                 uint4 k = make_uint4(0u, 0u, 0u, 0u);
                 if (t4 >= lo4 && t4 < hi4) {
                     const float4 v = __ldg(src0 + (size_t)c * hw4 + t4);
-                    k = make_uint4(orderable_u32(v.x, kNanKey), orderable_u32(v.y, kNanKey),
-                                   orderable_u32(v.z, kNanKey), orderable_u32(v.w, kNanKey));
+                    const bool sg = a.apply_sigmoid != 0;
+                    k = make_uint4(orderable_u32(act(v.x, sg), kNanKey), orderable_u32(act(v.y, sg), kNanKey),
+                                   orderable_u32(act(v.z, sg), kNanKey), orderable_u32(act(v.w, sg), kNanKey));
                 }
                 dst[i] = k;
             }
@@ -119,7 +130,7 @@ peak_candidates_kernel(DecodeArgs a) {
                 const float* src = hmb + (size_t)c * hw + (ptrdiff_t)y_lo * w;
                 uint32_t* dst = tkeys + (size_t)c * tplane;
                 for (int i = tid; i < tplane; i += kCandThreads)
-                    dst[i] = (i >= lo && i < hi) ? orderable_u32(__ldg(src + i), kNanKey) : 0u;
+                    dst[i] = (i >= lo && i < hi) ? orderable_u32(act(__ldg(src + i), a.apply_sigmoid != 0), kNanKey) : 0u;
             }
         }
     }
@@ -302,13 +313,14 @@ peak_select_kernel(DecodeArgs a) {
         const int y = sp / w;
         const int x = sp - y * w;
         const float* p = hmb + (size_t)c * hw + sp;
-        const uint32_t own = orderable_u32(__ldg(p), kNanKey);
+        const bool sg = a.apply_sigmoid != 0;
+        const uint32_t own = orderable_u32(act(__ldg(p), sg), kNanKey);
         uint32_t m = own;
         if (a.do_nms) {
             for (int dy = -1; dy <= 1; ++dy) {
                 if (y + dy < 0 || y + dy >= h) continue;
                 for (int dx = -1; dx <= 1; ++dx)
-                    if (x + dx >= 0 && x + dx < w) m = max(m, orderable_u32(__ldg(p + dy * w + dx), kNanKey));
+                    if (x + dx >= 0 && x + dx < w) m = max(m, orderable_u32(act(__ldg(p + dy * w + dx), sg), kNanKey));
             }
         }
         return ((unsigned long long)kept_key(own, m, a.do_nms != 0) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
@@ -373,8 +385,8 @@ peak_select_kernel(DecodeArgs a) {
             float xs, ys;
             if (a.off) {
                 const float* ob = a.off + (size_t)b * 2 * hw;
-                xs = __fadd_rn((float)x, ob[sp]);        // :85
-                ys = __fadd_rn((float)y, ob[hw + sp]);   // :86
+                xs = __fadd_rn((float)x, act(ob[sp], a.apply_sigmoid != 0));        // :85
+                ys = __fadd_rn((float)y, act(ob[hw + sp], a.apply_sigmoid != 0));   // :86
             } else {
                 xs = __fadd_rn((float)x, 0.5f);          // :88-89
                 ys = __fadd_rn((float)y, 0.5f);
@@ -419,8 +431,9 @@ nms_kernel(const float* __restrict__ heat, int planes, int h, int w, float* __re
 
 __global__ void __launch_bounds__(128)
 post_process_kernel(const float* __restrict__ det, int n, int num_classes, float down_ratio, float bsy, float bev_w,
-                    float bsx, float bev_h, float thresh, float* __restrict__ out, int32_t* __restrict__ cls,
-                    uint8_t* __restrict__ keep) {
+                    float bsx, float bev_h, float thresh, float min_x, float min_y, float min_z,
+                    float* __restrict__ out, int32_t* __restrict__ cls, uint8_t* __restrict__ keep,
+                    float* __restrict__ real) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* d = det + (size_t)i * 10;
@@ -438,6 +451,19 @@ post_process_kernel(const float* __restrict__ det, int n, int num_classes, float
     int c = (cf >= 0.0f && cf < (float)num_classes && cf == floorf(cf)) ? (int)cf : -1;
     cls[i] = c;
     keep[i] = (c >= 0 && score > thresh) ? 1 : 0;            // :134, :152
+    if (real) {
+        // convert_det_to_real_values, evaluation_utils.py:177-193: BEV pixels -> metres in the lidar
+        // frame, [cls, x, y, z, h, w, l, yaw]; every step rounds to fp32 like numpy's float32 scalars
+        float* r = real + (size_t)i * 8;
+        r[0] = cf;
+        r[1] = __fadd_rn(__fmul_rn(__fdiv_rn(o[2], bev_h), bsx), min_x);   // x <- y pixel, :185
+        r[2] = __fadd_rn(__fmul_rn(__fdiv_rn(o[1], bev_w), bsy), min_y);   // y <- x pixel, :186
+        r[3] = __fadd_rn(o[3], min_z);                                     // :187
+        r[4] = o[4];
+        r[5] = __fmul_rn(__fdiv_rn(o[5], bev_w), bsy);                     // :188
+        r[6] = __fmul_rn(__fdiv_rn(o[6], bev_h), bsx);                     // :189
+        r[7] = -o[7];                                                      // :184
+    }
 }
 
 size_t decode_workspace_bytes(int B, int C, int h, int w) {
@@ -503,12 +529,14 @@ extern "C" int sfa_decode_workspace_init(void* workspace, size_t workspace_bytes
 
 extern "C" int sfa_decode(const float* hm, const float* cen_offset, const float* direction, const float* z_coor,
                           const float* dim, int32_t B, int32_t C, int32_t h, int32_t w, int32_t K, float* det,
-                          int64_t* inds, void* workspace, size_t workspace_bytes, sfa_stream_t stream) {
+                          int64_t* inds, int32_t apply_sigmoid, void* workspace, size_t workspace_bytes,
+                          sfa_stream_t stream) {
     SFA_REQUIRE(B == 0 || (hm && direction && z_coor && dim && det), "NULL pointer argument");
     DecodeArgs a = {};
     a.hm = hm; a.off = cen_offset; a.dir = direction; a.zc = z_coor; a.dim = dim;
     a.B = B; a.C = C; a.h = h; a.w = w; a.K = K;
     a.do_nms = 1;
+    a.apply_sigmoid = apply_sigmoid ? 1 : 0;
     a.det = det; a.inds = inds;
     return launch_decode(a, workspace, workspace_bytes, (cudaStream_t)stream);
 }
@@ -539,15 +567,16 @@ extern "C" int sfa_nms(const float* heat, int32_t planes, int32_t h, int32_t w, 
 
 extern "C" int sfa_post_process(const float* det, int32_t B, int32_t K, int32_t num_classes, float down_ratio,
                                 float bound_size_y, float bev_width, float bound_size_x, float bev_height,
-                                float peak_thresh, float* out, int32_t* cls, uint8_t* keep, sfa_stream_t stream) {
+                                float peak_thresh, float min_x, float min_y, float min_z, float* out, int32_t* cls,
+                                uint8_t* keep, float* real, sfa_stream_t stream) {
     SFA_REQUIRE(B >= 0 && K >= 0, "bad shape B=%d K=%d", B, K);
     int n = B * K;
     if (n == 0) return SFA_OK;
     SFA_REQUIRE(det && out && cls && keep, "NULL pointer argument");
     SFA_LAUNCH("post_process", (cudaStream_t)stream,
                post_process_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-                   det, n, num_classes, down_ratio, bound_size_y, bev_width, bound_size_x, bev_height, peak_thresh, out,
-                   cls, keep));
+                   det, n, num_classes, down_ratio, bound_size_y, bev_width, bound_size_x, bev_height, peak_thresh, min_x,
+                   min_y, min_z, out, cls, keep, real));
     SFA_CUDA_TRY(cudaGetLastError());
     return SFA_OK;
 }

@@ -149,10 +149,13 @@ class DecodeWorkspace:
             _lib.check(lib.sfa_decode_workspace_init(ctypes.c_void_p(self.ptr), self.nbytes, _stream_ptr(self.device)))
 
 
-def decode_device(hm_cen, cen_offset, direction, z_coor, dim, K=40, out=None, inds=None, workspace=None):
+def decode_device(hm_cen, cen_offset, direction, z_coor, dim, K=40, out=None, inds=None, workspace=None,
+                  apply_sigmoid=False):
     """decode (utils/evaluation_utils.py:77-105) on CUDA float32 NCHW-contiguous heads, writing into
     `out` [B,K,10] (allocated when None) — no allocation, copy or sync when `out` is given, so the
-    call can be captured in a CUDA graph.  `inds` optional int64 [B,K] receives the spatial indices."""
+    call can be captured in a CUDA graph.  `inds` optional int64 [B,K] receives the spatial indices.
+    apply_sigmoid=True takes the backbone's RAW hm_cen / cen_offset logits and applies `_sigmoid`
+    (utils/torch_utils.py:44-45) while loading them (tolerance-level parity, see include/sfa_b200.h)."""
     lib = _lib.load()
     for name, t in (("hm_cen", hm_cen), ("direction", direction), ("z_coor", z_coor), ("dim", dim)):
         _require_cuda(t, name)
@@ -174,17 +177,20 @@ def decode_device(hm_cen, cen_offset, direction, z_coor, dim, K=40, out=None, in
         ws_ptr, ws_bytes = decode_workspace(hm_cen.device, B, C, h, w, K)
     with torch.cuda.device(hm_cen.device):
         rc = lib.sfa_decode(_ptr(hm_cen), _ptr(cen_offset), _ptr(direction), _ptr(z_coor), _ptr(dim), B, C, h, w, K,
-                            _ptr(out), _ptr(inds), ctypes.c_void_p(ws_ptr), ws_bytes, _stream_ptr(hm_cen.device))
+                            _ptr(out), _ptr(inds), 1 if apply_sigmoid else 0, ctypes.c_void_p(ws_ptr), ws_bytes,
+                            _stream_ptr(hm_cen.device))
     if rc != 0:
         # torch.topk raises RuntimeError when K > h*w (evaluation_utils.py:50): same exception type
         raise RuntimeError("decode: " + _lib.last_error())
     return out
 
 
-def post_process_dense(detections, num_classes=3, down_ratio=4, peak_thresh=0.2, cnf=None, out=None):
+def post_process_dense(detections, num_classes=3, down_ratio=4, peak_thresh=0.2, cnf=None, out=None, real=None):
     """Dense post_processing (utils/evaluation_utils.py:112-163) on CUDA detections [B,K,10]:
     returns (rows [B,K,8] f32, cls [B,K] i32, keep [B,K] u8/bool), all on the device.  With
-    `out=(rows, cls, keep_u8)` nothing is allocated (graph-capturable) and keep stays uint8."""
+    `out=(rows, cls, keep_u8)` nothing is allocated (graph-capturable) and keep stays uint8.
+    `real`: optional CUDA float32 [B,K,8] that receives convert_det_to_real_values (:177-193) of every
+    row (cls, x, y, z, h, w, l, yaw in metres), or True to allocate it; it is then returned as a 4th item."""
     from .config import kitti_config
     cnf = kitti_config if cnf is None else cnf
     lib = _lib.load()
@@ -197,11 +203,16 @@ def post_process_dense(detections, num_classes=3, down_ratio=4, peak_thresh=0.2,
         keep = torch.empty((B, K), dtype=torch.uint8, device=det.device)
     else:
         rows, cls, keep = out
+    if real is True:
+        real = torch.empty((B, K, 8), dtype=torch.float32, device=det.device)
+    b = cnf.boundary
     with torch.cuda.device(det.device):
         _lib.check(lib.sfa_post_process(_ptr(det), B, K, int(num_classes), float(down_ratio), float(cnf.bound_size_y),
                                         float(cnf.BEV_WIDTH), float(cnf.bound_size_x), float(cnf.BEV_HEIGHT),
-                                        float(peak_thresh), _ptr(rows), _ptr(cls), _ptr(keep), _stream_ptr(det.device)))
-    return (rows, cls, keep.bool()) if out is None else (rows, cls, keep)
+                                        float(peak_thresh), float(b["minX"]), float(b["minY"]), float(b["minZ"]),
+                                        _ptr(rows), _ptr(cls), _ptr(keep), _ptr(real), _stream_ptr(det.device)))
+    res = (rows, cls, keep.bool()) if out is None else (rows, cls, keep)
+    return res if real is None else res + (real,)
 
 
 class HostPipeline:

@@ -132,17 +132,24 @@ def post_processing(detections, num_classes=3, down_ratio=4, peak_thresh=0.2):
 
 
 def convert_det_to_real_values(detections, num_classes=3):
-    """BEV-pixel boxes -> metric lidar-frame boxes [cls, x, y, z, h, w, l, yaw] —
-    evaluation_utils.py:177-193 (<= K rows per frame; host arithmetic in the reference's own order)."""
-    kitti_dets = []
+    """BEV-pixel boxes -> metric lidar-frame boxes [cls, x, y, z, h, w, l, yaw] (one row per kept
+    detection, classes in order) — evaluation_utils.py:177-193.  `detections` is one sample's dict as
+    returned by post_processing.  Vectorised in float32, which is what numpy's float32 scalars give
+    step by step; the batched device form is fast.post_process_dense(..., real=True)."""
+    f = np.float32
+    out = []
     for cls_id in range(num_classes):
-        if len(detections[cls_id]) > 0:
-            for det in detections[cls_id]:
-                _score, _x, _y, _z, _h, _w, _l, _yaw = det
-                kitti_dets.append([cls_id,
-                                   _y / cnf.BEV_HEIGHT * cnf.bound_size_x + cnf.boundary["minX"],
-                                   _x / cnf.BEV_WIDTH * cnf.bound_size_y + cnf.boundary["minY"],
-                                   _z + cnf.boundary["minZ"], _h,
-                                   _w / cnf.BEV_WIDTH * cnf.bound_size_y,
-                                   _l / cnf.BEV_HEIGHT * cnf.bound_size_x, -_yaw])
-    return np.array(kitti_dets)
+        d = np.asarray(detections[cls_id], dtype=np.float32).reshape(-1, 8)
+        if d.shape[0] == 0:
+            continue
+        r = np.empty((d.shape[0], 8), dtype=np.float64)
+        r[:, 0] = cls_id
+        r[:, 1] = d[:, 2] / f(cnf.BEV_HEIGHT) * f(cnf.bound_size_x) + f(cnf.boundary["minX"])
+        r[:, 2] = d[:, 1] / f(cnf.BEV_WIDTH) * f(cnf.bound_size_y) + f(cnf.boundary["minY"])
+        r[:, 3] = d[:, 3] + f(cnf.boundary["minZ"])
+        r[:, 4] = d[:, 4]
+        r[:, 5] = d[:, 5] / f(cnf.BEV_WIDTH) * f(cnf.bound_size_y)
+        r[:, 6] = d[:, 6] / f(cnf.BEV_HEIGHT) * f(cnf.bound_size_x)
+        r[:, 7] = -d[:, 7]
+        out.append(r)
+    return np.concatenate(out, 0) if out else np.array([])

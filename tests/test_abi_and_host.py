@@ -54,7 +54,7 @@ def test_version_and_host_only_entry_points(built_lib):
     assert b"BEV size" in lib.sfa_last_error()
     assert lib.sfa_filter_workspace_bytes(120000) >= 4
     # argument validation happens before any CUDA call
-    rc = lib.sfa_decode(None, None, None, None, None, 1, 3, 152, 152, 50, None, None, None, 0, None)
+    rc = lib.sfa_decode(None, None, None, None, None, 1, 3, 152, 152, 50, None, None, 0, None, 0, None)
     assert rc == -1 and b"NULL" in lib.sfa_last_error()
     rc = lib.sfa_bev_rasterize(None, None, -1, 0, ctypes.byref(g.params), None, None, None, None, 0, None)
     assert rc == -1

@@ -231,3 +231,60 @@ def test_decode_full_batch_properties(cuda_device):
                         patch = hm[b, c[k], max(0, yy - 1):yy + 2, max(0, xx - 1):xx + 2]
                         found = found or patch.max() == g[b, k, 0]
             assert found
+
+
+def test_decode_fused_sigmoid_tolerance(cuda_device):
+    """`_sigmoid` (utils/torch_utils.py:44-45) applied to the raw hm_cen / cen_offset logits
+    inside the decode kernels.  torch's sigmoid and expf-based sigmoid agree to an ulp or two, so this path is held to
+    a tolerance (scores 2e-7 abs, boxes 1e-5) while the un-fused path stays bit-exact; detections whose score is not
+    within 1e-6 of a neighbour must be the same cells."""
+    fast = pkg("fast")
+    g = torch.Generator().manual_seed(21)
+    B = 8
+    hm_raw = torch.randn(B, 3, 152, 152, generator=g) * 2.0 - 2.0
+    hm_raw[:, :, 5:9, 5:9] = -20.0          # clamps to 1e-4: a plateau
+    hm_raw[0, 1, 40, 40] = 30.0             # clamps to 1 - 1e-4
+    off_raw = torch.randn(B, 2, 152, 152, generator=g)
+    _, _, d, z, dim = O.synth_heads(22, B=B)
+    want = O.decode(O._sigmoid(hm_raw.clone()), O._sigmoid(off_raw.clone()), d, z, dim, K=50).numpy()
+    got = fast.decode_device(hm_raw.to(cuda_device), off_raw.to(cuda_device), d.to(cuda_device), z.to(cuda_device),
+                             dim.to(cuda_device), K=50, apply_sigmoid=True).cpu().numpy()
+    np.testing.assert_allclose(got[:, :, 0], want[:, :, 0], rtol=0, atol=2e-7)
+    assert got[0, 0, 0] == np.float32(1 - 1e-4)
+    checked = 0
+    for b in range(B):
+        s = want[b, :, 0].astype(np.float64)
+        gap = np.minimum(np.abs(np.diff(s, prepend=np.inf)), np.abs(np.diff(s, append=-np.inf)))
+        for k in np.flatnonzero(gap > 1e-6):
+            np.testing.assert_allclose(got[b, k], want[b, k], rtol=1e-5, atol=1e-5)
+            assert got[b, k, 9] == want[b, k, 9]
+            checked += 1
+    assert checked > B * 40
+    # the flag off is the bit-exact path on already-activated heads
+    exact = fast.decode_device(O._sigmoid(hm_raw.clone()).to(cuda_device), O._sigmoid(off_raw.clone()).to(cuda_device),
+                               d.to(cuda_device), z.to(cuda_device), dim.to(cuda_device), K=50).cpu().numpy()
+    assert np.array_equal(_bits(O.canonical_detections(exact)), _bits(O.canonical_detections(want)))
+
+
+def test_convert_det_to_real_values_device_and_host(cuda_device):
+    """convert_det_to_real_values (evaluation_utils.py:177-193), dense on the device and
+    as the reference-signature host function, against the reference's own output (golden) and the oracle."""
+    fast = pkg("fast")
+    z = np.load(os.path.join(GOLD, "decode_small.npz"))
+    det = z["d0_det"].astype(np.float32)
+    pp = _ev().post_processing(det, 3, 4, 0.2)
+    host = _ev().convert_det_to_real_values(pp[0])
+    np.testing.assert_allclose(np.asarray(host, np.float64).reshape(-1, 8), z["d0_real_s0"], rtol=1e-6, atol=1e-6)
+    rows, cls, keep, real = fast.post_process_dense(torch.from_numpy(det).to(cuda_device), real=True)
+    real, cls, keep = real.cpu().numpy(), cls.cpu().numpy(), keep.cpu().numpy()
+    dense = np.concatenate([real[0][(cls[0] == j) & keep[0]] for j in range(3)], 0)
+    np.testing.assert_allclose(dense.astype(np.float64), z["d0_real_s0"], rtol=1e-6, atol=1e-6)
+    heads = O.synth_heads(33, B=5, tie_free=True)
+    det5 = O.decode(*[t.clone() for t in heads], K=50).numpy().astype(np.float32)
+    rows, cls, keep, real = fast.post_process_dense(torch.from_numpy(det5).to(cuda_device), real=True)
+    ref_pp = O.post_processing(det5)
+    for i in range(5):
+        want = np.asarray(O.convert_det_to_real_values(ref_pp[i]), np.float64).reshape(-1, 8)
+        r, c, k = real[i].cpu().numpy(), cls[i].cpu().numpy(), keep[i].cpu().numpy()
+        got = np.concatenate([r[(c == j) & k] for j in range(3)], 0)
+        np.testing.assert_allclose(got.astype(np.float64), want, rtol=1e-5, atol=1e-5)
