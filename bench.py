@@ -448,45 +448,69 @@ def run_b200(args):
         pts_pin = pin(pts_h.reshape(-1, 4))
         heads_pin = tuple(t.contiguous().pin_memory() for t in heads_h)
         offs_h = (np.arange(B + 1, dtype=np.int64) * N_POINTS)
-        bev_pin = torch.empty((B, 3, BEV_H, BEV_W), dtype=torch.float32).pin_memory()
-        det_pin = torch.empty((B, TOPK, 10), dtype=torch.float32).pin_memory()
-        pl = fast.HostPipeline(geom, max_frames=B, max_points=N_POINTS, C=0, h=1, w=1, K=1, device=local_rank)
-
-        # two pipelines (own streams and staging buffers), driven from two host threads: the decode's
-        # uploads overlap the BEV maps' downloads (PCIe is full duplex; ctypes releases the GIL)
-        pl2 = fast.HostPipeline(geom, max_frames=B, max_points=0, C=HEAD_C, h=HEAD_H, w=HEAD_W, K=TOPK, device=local_rank)
+        # `pipelines` independent workers (host threads), each with a BEV pipeline and a decode pipeline of
+        # its own (own streams, staging buffers, pinned outputs), take the steps in turn: within a step the
+        # decode's uploads overlap the BEV maps' downloads (PCIe is full duplex; ctypes releases the GIL),
+        # and one step's uploads overlap the previous step's downloads.
         from concurrent.futures import ThreadPoolExecutor
-        pool = ThreadPoolExecutor(max_workers=1)
-        pts_np, bev_np, det_np = pts_pin.numpy(), bev_pin.numpy(), det_pin.numpy()
+        n_work = max(1, args.pipelines)
+        pts_np = pts_pin.numpy()
         heads_np = [t.numpy() for t in heads_pin]
 
-        def e2e_step():
-            fut = pool.submit(pl2.decode, *heads_np, out=det_np)
-            pl.bev(pts_np, offs_h, out=bev_np)
-            fut.result()
+        class HostWorker:
+            def __init__(self):
+                self.bev = fast.HostPipeline(geom, max_frames=B, max_points=N_POINTS, C=0, h=1, w=1, K=1, device=local_rank)
+                self.dec = fast.HostPipeline(geom, max_frames=B, max_points=0, C=HEAD_C, h=HEAD_H, w=HEAD_W, K=TOPK,
+                                             device=local_rank)
+                self.bev_out = torch.empty((B, 3, BEV_H, BEV_W), dtype=torch.float32).pin_memory().numpy()
+                self.det_out = torch.empty((B, TOPK, 10), dtype=torch.float32).pin_memory().numpy()
+                self.side = ThreadPoolExecutor(max_workers=1)
 
-        e2e_steps = max(1, min(args.steps, 200))
-        for _ in range(3):
-            e2e_step()
+            def step(self):
+                fut = self.side.submit(self.dec.decode, *heads_np, out=self.det_out)
+                self.bev.bev(pts_np, offs_h, out=self.bev_out)
+                fut.result()
+
+            def run(self, n):
+                for _ in range(n):
+                    self.step()
+
+            def close(self):
+                self.side.shutdown()
+                self.bev.close()
+                self.dec.close()
+
+        workers = [HostWorker() for _ in range(n_work)]
+        pool = ThreadPoolExecutor(max_workers=n_work)
+        e2e_steps = max(n_work, min(args.steps, 200))
+        share = [e2e_steps // n_work + (1 if i < e2e_steps % n_work else 0) for i in range(n_work)]
+        list(pool.map(lambda w: w.run(2), workers))   # warm-up
         barrier()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
+        list(pool.map(lambda wn: wn[0].run(wn[1]), zip(workers, share)))
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if world > 1:
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        bev_pin, det_pin = torch.from_numpy(workers[0].bev_out), torch.from_numpy(workers[0].det_out)
+        # the host path must deliver what the device path computes for the same inputs (set 0)
+        engines[0].step_serial(0)
+        torch.cuda.synchronize()
+        e2e_ok = bool(torch.equal(engines[0].bev_out.cpu(), bev_pin) and torch.equal(engines[0].det_out.cpu(), det_pin))
+        if not e2e_ok:
+            raise SystemExit("e2e outputs differ from the device-resident path")
         h2d = pts_pin.numel() * 4 + sum(t.numel() * 4 for t in heads_pin) + offs_h.nbytes
         d2h = bev_pin.numel() * 4 + det_pin.numel() * 4
         e2e = {"value": round(B * e2e_steps * world / dt, 1), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": round(dt / e2e_steps * 1e3, 4), "steps": e2e_steps,
+               "outputs_equal_device_path": e2e_ok,
                "api": "sfa_pipeline_bev_host + sfa_pipeline_decode_host (pinned host sweeps/heads in, host BEV maps + "
-                      "detections out)"}
+                      "detections out), %d host workers taking steps in turn" % n_work}
         pool.shutdown()
-        pl.close()
-        pl2.close()
+        for wk in workers:
+            wk.close()
 
     if rank == 0:
         line = {
