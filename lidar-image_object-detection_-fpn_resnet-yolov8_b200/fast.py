@@ -55,15 +55,21 @@ class BevRasterizer:
                                                        _stream_ptr(self.device)))
 
     def __call__(self, points, offsets, max_points, out=None):
-        """points [total,4] f32 cuda, offsets [B+1] i64 cuda, max_points: python int upper bound on
-        the points of any sweep.  Returns out [B,3,H,W] f32 (channel 0 intensity, 1 height, 2 density)."""
+        """points [total,4] f32 cuda, offsets [B+1] i64 cuda (or None for a uniform batch of sweeps with
+        exactly max_points points each), max_points: python int upper bound on the points of any sweep.
+        Returns out [B,3,H,W] f32 (channel 0 intensity, 1 height, 2 density)."""
         _require_cuda(points, "points")
-        _require_cuda(offsets, "offsets")
-        if points.dtype != torch.float32 or offsets.dtype != torch.int64:
-            raise TypeError("points must be float32 and offsets int64")
-        if not points.is_contiguous() or not offsets.is_contiguous():
-            raise ValueError("points / offsets must be contiguous")
-        B = offsets.numel() - 1
+        if points.dtype != torch.float32 or not points.is_contiguous():
+            raise TypeError("points must be contiguous float32")
+        if offsets is None:      # uniform batch: every sweep holds exactly max_points points
+            if int(max_points) <= 0 or points.numel() % (4 * int(max_points)):
+                raise ValueError("a uniform batch needs total_points to be a multiple of max_points")
+            B = points.numel() // (4 * int(max_points))
+        else:
+            _require_cuda(offsets, "offsets")
+            if offsets.dtype != torch.int64 or not offsets.is_contiguous():
+                raise TypeError("offsets must be contiguous int64")
+            B = offsets.numel() - 1
         g = self.geom
         if int(max_points) > self.max_points:
             raise ValueError("max_points %d exceeds the %d this rasteriser's workspace was sized for"
@@ -78,10 +84,9 @@ class BevRasterizer:
         return out
 
     def rasterize_uniform(self, points, out=None):
-        """points [B,N,4]: every sweep has N points."""
-        B, N = points.shape[0], points.shape[1]
-        offsets = torch.arange(B + 1, dtype=torch.int64, device=points.device) * N
-        return self(points.reshape(-1, 4), offsets, N, out=out)
+        """points [B,N,4]: every sweep has N points (no offsets array, no dependent load in the kernels)."""
+        N = points.shape[1]
+        return self(points.reshape(-1, 4), None, N, out=out)
 
     def out_of_map_points(self, reset=True):
         """Points seen since the last reset whose cell index fell outside the (H+1)x(W+1) map (the

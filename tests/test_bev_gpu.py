@@ -256,3 +256,18 @@ def test_host_pipeline_and_dropin_makeBEVMap(cuda_device):
     for i, s in enumerate(sweeps):
         _assert_bit_exact(out[i], O.make_bev_scatter(s, O.KITTI, True, np.float32), "host frame %d" % i)
     pl.close()
+
+
+@pytest.mark.parametrize("algorithm", ALGOS)
+def test_bev_uniform_batch_without_offsets(cuda_device, algorithm):
+    """offsets = NULL: every sweep holds exactly max_points points (the batched API's uniform form)."""
+    fast = pkg("fast")
+    B, N = 5, 30000
+    sweeps = [O.synth_sweep(600 + i, N, O.KITTI, k) for i, k in enumerate(["uniform", "zties", "outside", "bounds", "clustered"])]
+    pts = torch.from_numpy(np.stack(sweeps)).to(cuda_device)
+    rast = fast.BevRasterizer(_geom(O.KITTI, algorithm=algorithm), max_batch=B, max_points=N, device=cuda_device)
+    got = rast.rasterize_uniform(pts).cpu().numpy()
+    for i, s in enumerate(sweeps):
+        _assert_bit_exact(got[i], O.make_bev_scatter(s, O.KITTI, True, np.float32), "uniform frame %d" % i)
+    with pytest.raises(ValueError):
+        rast(pts.reshape(-1, 4)[:-1], None, N)
