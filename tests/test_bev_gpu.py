@@ -271,3 +271,69 @@ def test_bev_uniform_batch_without_offsets(cuda_device, algorithm):
         _assert_bit_exact(got[i], O.make_bev_scatter(s, O.KITTI, True, np.float32), "uniform frame %d" % i)
     with pytest.raises(ValueError):
         rast(pts.reshape(-1, 4)[:-1], None, N)
+
+
+def test_bev_concurrent_streams_share_no_state(cuda_device):
+    """Two rasterisers (own workspaces) driven concurrently from two CUDA streams, repeatedly: the library keeps
+    no hidden global device state, so both results stay bit-exact."""
+    fast = pkg("fast")
+    sweeps_a = [O.synth_sweep(700 + i, 90000, O.KITTI, "zties") for i in range(6)]
+    sweeps_b = [O.synth_sweep(800 + i, 70000, O.KITTI, "clustered") for i in range(6)]
+    ra = fast.BevRasterizer(_geom(O.KITTI), max_batch=6, max_points=90000, device=cuda_device)
+    rb = fast.BevRasterizer(_geom(O.KITTI), max_batch=6, max_points=70000, device=cuda_device)
+    pa = torch.from_numpy(np.stack(sweeps_a)).to(cuda_device)
+    pb = torch.from_numpy(np.stack(sweeps_b)).to(cuda_device)
+    sa, sb = torch.cuda.Stream(device=cuda_device), torch.cuda.Stream(device=cuda_device)
+    torch.cuda.synchronize()
+    for _ in range(5):
+        with torch.cuda.stream(sa):
+            oa = ra.rasterize_uniform(pa)
+        with torch.cuda.stream(sb):
+            ob = rb.rasterize_uniform(pb)
+    torch.cuda.synchronize()
+    for i in range(6):
+        _assert_bit_exact(oa[i].cpu().numpy(), O.make_bev_scatter(sweeps_a[i], O.KITTI, True, np.float32), "stream a %d" % i)
+        _assert_bit_exact(ob[i].cpu().numpy(), O.make_bev_scatter(sweeps_b[i], O.KITTI, True, np.float32), "stream b %d" % i)
+
+
+def test_bev_and_decode_in_a_cuda_graph(cuda_device):
+    """The device API allocates nothing and never synchronises: a whole BEV + decode + post-process step captures
+    into one CUDA graph and replays with new inputs in the same buffers."""
+    fast = pkg("fast")
+    B, N = 4, 50000
+    rast = fast.BevRasterizer(_geom(O.KITTI), max_batch=B, max_points=N, device=cuda_device)
+    pts = torch.empty((B, N, 4), dtype=torch.float32, device=cuda_device)
+    heads = [torch.empty_like(t, device=cuda_device) for t in O.synth_heads(0, B=B)]
+    bev = torch.empty((B, 3, 608, 608), dtype=torch.float32, device=cuda_device)
+    det = torch.empty((B, 50, 10), dtype=torch.float32, device=cuda_device)
+    pp = (torch.empty((B, 50, 8), device=cuda_device), torch.empty((B, 50), dtype=torch.int32, device=cuda_device),
+          torch.empty((B, 50), dtype=torch.uint8, device=cuda_device))
+    ws = fast.DecodeWorkspace(cuda_device, B, 3, 152, 152, 50)
+
+    def step():
+        rast.rasterize_uniform(pts, out=bev)
+        fast.decode_device(*heads, K=50, out=det, workspace=ws)
+        fast.post_process_dense(det, out=pp)
+
+    def load(seed):
+        sweeps = [O.synth_sweep(seed * 10 + i, N, O.KITTI, "zties") for i in range(B)]
+        hh = O.synth_heads(seed, B=B, tie_free=True)
+        pts.copy_(torch.from_numpy(np.stack(sweeps)))
+        for dst, src in zip(heads, hh):
+            dst.copy_(src)
+        return sweeps, hh
+
+    load(1)
+    step()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        step()
+    for seed in (2, 3):
+        sweeps, hh = load(seed)
+        g.replay()
+        torch.cuda.synchronize()
+        for i in range(B):
+            _assert_bit_exact(bev[i].cpu().numpy(), O.make_bev_scatter(sweeps[i], O.KITTI, True, np.float32), "graph %d" % i)
+        want = O.decode(*[t.clone() for t in hh], K=50).numpy()
+        assert np.array_equal(det.cpu().numpy().view(np.uint32), want.view(np.uint32))
