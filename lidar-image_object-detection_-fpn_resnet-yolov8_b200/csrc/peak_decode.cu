@@ -40,6 +40,8 @@ constexpr int kCandWarps = kCandThreads / 32;
 constexpr int kCandRows = 16;              // rows of a slab
 constexpr int kSelThreads = 1024;
 constexpr int kSelSmemItems = 12288;       // candidate words selected from shared memory (96 KB)
+constexpr int kSelUnroll = 4;              // list entries a select thread loads before it processes them
+constexpr int kSelTieWindow = 8192;        // tie-break shortcut: tied cells with a linear index below this
 constexpr int kMaxK = 128;
 constexpr uint32_t kNanKey = 0xFFFFFFFFu;  // torch.topk ranks NaN above everything
 constexpr uint32_t kZeroKey = 0x80000000u, kPosInfKey = 0xFF800000u, kNegInfKey = 0x007FFFFFu;
@@ -227,7 +229,8 @@ struct SelectShared {
 // on return sh.prefix is the 32-bit value of the need-th largest word, sh.need how many of the words
 // EQUAL to it belong to the top `need`, and sh.eqpop how many words equal it.  All threads call.
 // PEEL: aggregate the warp's most common bins (huge tie groups) instead of one atomic per lane.
-template <bool PEEL, class WordFn>
+// UNROLL: list entries a thread loads before it processes them (memory-level parallelism for lists in L2).
+template <bool PEEL, int UNROLL, class WordFn>
 __device__ void block_radix_select(WordFn word, int n, unsigned need, SelectShared& sh) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) { sh.prefix = 0; sh.need = need; sh.eqpop = 0; }
@@ -238,13 +241,21 @@ __device__ void block_radix_select(WordFn word, int n, unsigned need, SelectShar
         for (int i = tid; i < 256; i += kSelThreads) sh.hist[i] = 0;
         __syncthreads();
         const uint32_t prefix = sh.prefix;
-        for (int base = 0; base < n; base += kSelThreads) {
-            const int i = base + tid;
-            bool active = false;
-            uint32_t k = 0;
-            if (i < n) active = word(i, k) && ((k ^ prefix) & himask) == 0;
-            if (PEEL) hist_add(sh.hist, active, (k >> shift) & 255u, lane);
-            else if (active) atomicAdd(&sh.hist[(k >> shift) & 255u], 1u);
+        for (int base = 0; base < n; base += UNROLL * kSelThreads) {   // block-uniform trip count
+            bool active[UNROLL];
+            uint32_t k[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {   // UNROLL independent loads in flight per thread
+                const int i = base + u * kSelThreads + tid;
+                k[u] = 0;
+                active[u] = (i < n) && word(i, k[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const bool a = active[u] && ((k[u] ^ prefix) & himask) == 0;
+                if (PEEL) hist_add(sh.hist, a, (k[u] >> shift) & 255u, lane);
+                else if (a) atomicAdd(&sh.hist[(k[u] >> shift) & 255u], 1u);
+            }
         }
         __syncthreads();
         if (warp == 0) {
@@ -284,7 +295,7 @@ peak_select_kernel(DecodeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ SelectShared sel;
     __shared__ unsigned long long surv[kMaxK];
-    __shared__ unsigned int n_surv;
+    __shared__ unsigned int n_surv, n_small;
     unsigned long long* scand = reinterpret_cast<unsigned long long*>(smem_raw);
     const int b = blockIdx.x;
     const int C = a.C, h = a.h, w = a.w, K = a.K;
@@ -332,31 +343,83 @@ peak_select_kernel(DecodeArgs a) {
     // shared memory holds positive peaks whose scores are spread over many bins: plain shared
     // atomics; the long lists / whole maps are dominated by a few values: peel them.
     auto hi_word = [&](int i, uint32_t& k) { k = (uint32_t)(item(i) >> 32); return true; };
-    if (mode == 0) block_radix_select<false>(hi_word, n, (unsigned)K, sel);
-    else           block_radix_select<true>(hi_word, n, (unsigned)K, sel);
+    if (mode == 0) block_radix_select<false, 1>(hi_word, n, (unsigned)K, sel);
+    else           block_radix_select<true, kSelUnroll>(hi_word, n, (unsigned)K, sel);
     const uint32_t thr_hi = sel.prefix;
     uint32_t thr_lo = 0;
     const bool straddle = sel.eqpop > sel.need;
     const unsigned need_eq = sel.need;
     __syncthreads();
     if (straddle) {
-        auto lo_word = [&](int i, uint32_t& k) {
-            const unsigned long long v = item(i);
-            k = (uint32_t)v;
-            return (uint32_t)(v >> 32) == thr_hi;
-        };
-        // index words are distinct but share their leading bytes (indices are < C*h*w): the first
-        // passes put every tied cell into one bin, so aggregate
-        block_radix_select<true>(lo_word, n, need_eq, sel);
-        thr_lo = sel.prefix;
-        __syncthreads();
+        // Of the cells that tie at the K-th score the need_eq LOWEST linear indices win.  When the tie
+        // group is huge (a plateau: most of the map) they all sit at the very start of the map, so one
+        // pass first gathers the tied cells with an index below kSelTieWindow into shared memory; if
+        // there are at least need_eq of them the 4-pass select runs on that short list, else on everything.
+        bool done = false;
+        if (mode != 0) {   // (mode 0: the whole list already sits in shared memory)
+            if (tid == 0) n_small = 0;
+            __syncthreads();
+            const uint32_t lo_min = 0xFFFFFFFFu - (uint32_t)(kSelTieWindow - 1);   // lo word of index kSelTieWindow-1
+            for (int base = 0; base < n; base += kSelUnroll * kSelThreads) {
+                unsigned long long v[kSelUnroll];
+#pragma unroll
+                for (int u = 0; u < kSelUnroll; ++u) {
+                    const int i = base + u * kSelThreads + tid;
+                    v[u] = i < n ? item(i) : 0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < kSelUnroll; ++u)
+                    if ((uint32_t)(v[u] >> 32) == thr_hi && (uint32_t)v[u] >= lo_min && v[u] != 0ull) {
+                        const unsigned pos = atomicAdd(&n_small, 1u);
+                        if (pos < (unsigned)kSelSmemItems) scand[pos] = v[u];
+                    }
+            }
+            __syncthreads();
+            const unsigned ns = n_small;
+            if (ns >= need_eq && ns <= (unsigned)kSelSmemItems) {
+                block_radix_select<true, 1>([&](int i, uint32_t& k) { k = (uint32_t)scand[i]; return true; }, (int)ns, need_eq, sel);
+                thr_lo = sel.prefix;
+                done = true;
+                __syncthreads();
+            }
+        }
+        if (!done) {
+            auto lo_word = [&](int i, uint32_t& k) {
+                const unsigned long long v = item(i);
+                k = (uint32_t)v;
+                return (uint32_t)(v >> 32) == thr_hi;
+            };
+            // index words are distinct but share their leading bytes (indices are < C*h*w): the first
+            // passes put every tied cell into one bin, so aggregate
+            if (mode == 0) block_radix_select<true, 1>(lo_word, n, need_eq, sel);
+            else           block_radix_select<true, kSelUnroll>(lo_word, n, need_eq, sel);
+            thr_lo = sel.prefix;
+            __syncthreads();
+        }
     }
     const unsigned long long thr = ((unsigned long long)thr_hi << 32) | thr_lo;
-    for (int i = tid; i < n; i += kSelThreads) {
-        const unsigned long long v = item(i);
-        if (v >= thr) {
-            const unsigned pos = atomicAdd(&n_surv, 1u);
-            if (pos < (unsigned)kMaxK) surv[pos] = v;
+    if (mode == 0) {
+        for (int i = tid; i < n; i += kSelThreads) {
+            const unsigned long long v = scand[i];
+            if (v >= thr) {
+                const unsigned pos = atomicAdd(&n_surv, 1u);
+                if (pos < (unsigned)kMaxK) surv[pos] = v;
+            }
+        }
+    } else {
+        for (int base = 0; base < n; base += kSelUnroll * kSelThreads) {
+            unsigned long long v[kSelUnroll];
+#pragma unroll
+            for (int u = 0; u < kSelUnroll; ++u) {
+                const int i = base + u * kSelThreads + tid;
+                v[u] = i < n ? item(i) : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < kSelUnroll; ++u)
+                if (v[u] >= thr && v[u] != 0ull) {
+                    const unsigned pos = atomicAdd(&n_surv, 1u);
+                    if (pos < (unsigned)kMaxK) surv[pos] = v[u];
+                }
         }
     }
     __syncthreads();
