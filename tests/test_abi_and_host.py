@@ -45,7 +45,8 @@ def test_version_and_host_only_entry_points(built_lib):
     assert ctypes.sizeof(g.params) == 52          # struct SfaBevParams: 9 floats + 4 int32
     n1 = lib.sfa_bev_workspace_bytes(1, 120000, ctypes.byref(g.params))
     n64 = lib.sfa_bev_workspace_bytes(64, 120000, ctypes.byref(g.params))
-    assert n1 >= 64 * 120000 * 16 and n64 >= n1 and n64 < (4 << 30)
+    # tiled: per ring frame 64 buckets of 8x the even share (15008 records) + one overflow list of max_points records
+    assert n1 >= (64 * 15008 + 120000) * 16 and n64 >= n1 and n64 < (1 << 30)
     ga = pkg("geometry").from_config(pkg("config.kitti_config"), algorithm=pkg("_lib").BEV_GLOBAL_ATOMIC)
     na = lib.sfa_bev_workspace_bytes(64, 120000, ctypes.byref(ga.params))
     assert 608 * 608 * 12 <= na < (1 << 30)

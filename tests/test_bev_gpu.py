@@ -167,6 +167,29 @@ def test_bev_max_height_not_a_power_of_two(cuda_device, algorithm):
     _assert_bit_exact(got[0], ref.astype(np.float32), "max_h=3 vs lexsort port")
 
 
+def test_bev_bucket_overflow_paths(cuda_device):
+    """A band's bucket holds 8x the even share of a sweep; what does not fit goes to the frame's overflow list.
+    Sweeps concentrated in one band / two bands / one cell overflow massively; mixed with ordinary frames in one batch
+    (the overflow counters are per ring frame and reset per chunk), run twice on the same workspace."""
+    rng = np.random.default_rng(11)
+    b = O.KITTI.boundary
+
+    def strip(n, x_lo, x_hi, zq=8):
+        return np.stack([rng.uniform(x_lo, x_hi, n), rng.uniform(b["minY"], b["maxY"], n),
+                         np.round(rng.uniform(b["minZ"], b["maxZ"], n) * zq) / zq, rng.uniform(0, 1, n)], 1).astype(np.float32)
+
+    sweeps = [strip(120000, 20.0, 20.7),                                   # one band: ~105k records overflow
+              O.synth_sweep(901, 120000, O.KITTI, "uniform"),
+              np.concatenate([strip(60000, 3.0, 3.5), strip(60000, 44.0, 44.6)]),   # two overflowing bands
+              O.synth_sweep(902, 100000, O.KITTI, "onecell"),
+              strip(120000, 0.0, 6.0, zq=2),                               # 8 bands, each about at its bucket's capacity
+              O.synth_sweep(903, 50000, O.KITTI, "zties")]
+    for attempt in range(2):
+        got, _ = _run_batch(cuda_device, sweeps, O.KITTI, algorithm=TILED)
+        for i, s in enumerate(sweeps):
+            _assert_bit_exact(got[i], O.make_bev_scatter(s, O.KITTI, True, np.float32), "overflow frame %d" % i)
+
+
 def test_bev_crowded_band_streams_records(cuda_device):
     """More records in one band than its threads hold in registers (8 x 512): the band kernel
     re-reads them from L2 once per phase.  Also a single cell holding > 63 points (LUT saturation)."""
