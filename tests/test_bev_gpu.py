@@ -136,11 +136,11 @@ def test_bev_odd_grid_scalar_finalize(cuda_device):
     _assert_bit_exact(got[0], O.make_bev_scatter(sweep, g, True, np.float32), "301x301")
 
 
-@pytest.mark.parametrize("geomspec", [(304, 304), (1000, 1000), (2400, 2400), (3000, 3000), (100, 36)])
+@pytest.mark.parametrize("geomspec", [(304, 304), (1000, 1000), (1700, 1700), (2400, 2400), (100, 36)])
 def test_bev_other_grids_tiled_band_plans(cuda_device, geomspec):
-    """Other map sizes exercise other band plans of the tiled path (fewer / more than 64 bands, a last
-    band that is partly outside the map; 2400^2 needs 979 bands) and, at 3000^2 (> 2^23 cells), the
-    automatic switch to the global-atomic path; 1000^2 is the grid the literal Argoverse DISCRETIZATION=0.1 implies (argoverse_config.py:10)."""
+    """Other map sizes exercise other band plans of the tiled path (fewer / more than 128 bands, a last
+    band that is partly outside the map; 1700^2 needs 982 bands) and, at 2400^2 (more cells than 1024 bands
+    hold), the automatic switch to the global-atomic path; 1000^2 is the grid the literal Argoverse DISCRETIZATION=0.1 implies (argoverse_config.py:10)."""
     H, W = geomspec
     g = O.Geometry(boundary={"minX": 0, "maxX": 40, "minY": -20, "maxY": 20, "minZ": -2, "maxZ": 2},
                    BEV_HEIGHT=H, BEV_WIDTH=W, DISCRETIZATION=40 / H)
