@@ -44,12 +44,29 @@ void profile_mark(const char* name, cudaStream_t stream, bool begin);
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// ---- L2 eviction policy for write-once / read-once streams ---------------------------------------
+// The sweeps (read once) and the BEV planes (written once) stream THROUGH the L2, while the point
+// records in between are written by bev_bin and read back by bev_band microseconds later: marking
+// the streams evict-first keeps them from pushing the records out to HBM.
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
 // ---- streaming memory access (data a CTA touches exactly once: keep it out of L1) ----
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
     float4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                  : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ld_stream_f4_evict_first(const float4* p, unsigned long long pol) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p), "l"(pol));
     return v;
 }
 __device__ __forceinline__ void st_stream_f4(float4* p, const float4& v) {
@@ -67,6 +84,11 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr_u32(ssrc)),
                  "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store_s2g_hint(void* gdst, const void* ssrc, uint32_t bytes, unsigned long long pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+                 "r"(smem_addr_u32(ssrc)), "r"(bytes), "l"(pol)
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
