@@ -46,6 +46,7 @@ PROTOTYPES = {
                                          ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(i32)]),
     "sfa_bev_rasterize": (ctypes.c_int, [c_void_p, c_void_p, i32, i64, ctypes.POINTER(SfaBevParams), c_void_p,
                                          c_void_p, c_void_p, c_void_p, sz, c_void_p]),
+    "sfa_selftest_division": (ctypes.c_int, [f32, ctypes.c_uint32, ctypes.c_uint64, c_void_p, c_void_p]),
     "sfa_filter_workspace_bytes": (sz, [i64]),
     "sfa_filter_lidar": (ctypes.c_int, [c_void_p, i64, ctypes.POINTER(SfaBevParams), c_void_p, c_void_p, c_void_p,
                                         sz, c_void_p]),

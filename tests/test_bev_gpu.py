@@ -360,3 +360,20 @@ def test_bev_and_decode_in_a_cuda_graph(cuda_device):
             _assert_bit_exact(bev[i].cpu().numpy(), O.make_bev_scatter(sweeps[i], O.KITTI, True, np.float32), "graph %d" % i)
         want = O.decode(*[t.clone() for t in hh], K=50).numpy()
         assert np.array_equal(det.cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("d", [50 / 608, 100 / 608, 0.1, 40 / 1000, 1.0, 3.0, 1e-3])
+def test_exact_division_matches_div_rn_over_every_float_in_range(cuda_device, d):
+    """The hoisted-reciprocal division of bev_bin against the compiler's IEEE div.rn for EVERY float in
+    [2^-30, 2^12) and its negative (2.8e8 bit patterns per sign, covers every coordinate a map can index), plus a
+    stretch of denormals / tiny values and of huge values / inf / NaN where the routine must fall back."""
+    import ctypes
+    lib = pkg("_lib").load()
+    bad = torch.zeros(1, dtype=torch.int64, device=cuda_device)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(cuda_device).cuda_stream)
+    d32 = float(np.float32(d))
+    lo, hi = np.float32(2.0 ** -30).view(np.uint32), np.float32(2.0 ** 12).view(np.uint32)
+    for first, count in ((int(lo), int(hi) - int(lo)), (0, 1 << 24), (int(np.float32(2.0 ** 90).view(np.uint32)), (0x7FC00010 - int(np.float32(2.0 ** 90).view(np.uint32))))):
+        pkg("_lib").check(lib.sfa_selftest_division(d32, first, count, ctypes.c_void_p(bad.data_ptr()), stream))
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0

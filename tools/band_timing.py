@@ -1,5 +1,5 @@
 import sys, ctypes, importlib, numpy as np, torch
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/oracle')
+import os; ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 import sfa_oracle as O
 P = "lidar-image_object-detection_-fpn_resnet-yolov8_b200"
 fast = importlib.import_module(P + ".fast"); lib = importlib.import_module(P + "._lib").load()

@@ -1,6 +1,6 @@
 """Decode timing on plateau-heavy heat maps (sigmoid outputs clamped at 1e-4) vs spread scores."""
 import sys, importlib, torch
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/oracle')
+import os; ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 import sfa_oracle as O
 fast = importlib.import_module("lidar-image_object-detection_-fpn_resnet-yolov8_b200.fast")
 dev = torch.device('cuda', 0)

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Runs on the GPU box (under gpurun): plain run, then (optionally) the ncu launch list and one full
 # capture of the kernels matching $1 (regex) of the same command.  Outputs land in gpurun_out/.
-#   ./tools_gpu_profile.sh 'decode_kernel|bev_band_kernel|bev_bin_kernel' 9 [list]
+#   tools/gpu_profile.sh 'decode_kernel|bev_band_kernel|bev_bin_kernel' 9 [list]
 set -u
 PAT="${1:-decode_kernel|bev_band_kernel|bev_bin_kernel}"
 COUNT="${2:-9}"

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Reads an ncu report's source page (SASS) for one kernel and prints the instructions that collect the
-most warp-stall samples, with the dominant stall reason.  Usage: tools_ncu_hot.py report.ncu-rep regex [top]"""
+most warp-stall samples, with the dominant stall reason.  Usage: tools/ncu_hot.py report.ncu-rep regex [top]"""
 import csv
 import subprocess
 import sys
