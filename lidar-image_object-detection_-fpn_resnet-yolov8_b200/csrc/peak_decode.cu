@@ -114,9 +114,9 @@ peak_candidates_kernel(DecodeArgs a) {
             const int hw4 = hw >> 2;
             const float4* src0 = reinterpret_cast<const float4*>(hmb) + (ptrdiff_t)y_lo * w4;
             uint4* dst = reinterpret_cast<uint4*>(tkeys);
+            int c = 0, t4 = tid;   // flat index i = c * tplane4 + t4, advanced without a division
+            while (t4 >= tplane4 && c < C) { t4 -= tplane4; ++c; }
             for (int i = tid; i < C * tplane4; i += kCandThreads) {   // all classes in one flat loop
-                const int c = i / tplane4;
-                const int t4 = i - c * tplane4;
                 uint4 k = make_uint4(0u, 0u, 0u, 0u);
                 if (t4 >= lo4 && t4 < hi4) {
                     const float4 v = __ldg(src0 + (size_t)c * hw4 + t4);
@@ -125,6 +125,8 @@ peak_candidates_kernel(DecodeArgs a) {
                                    orderable_u32(act(v.z, sg), kNanKey), orderable_u32(act(v.w, sg), kNanKey));
                 }
                 dst[i] = k;
+                t4 += kCandThreads;
+                while (t4 >= tplane4) { t4 -= tplane4; ++c; }
             }
         } else {
             const int lo = tr_first * w, hi = tr_end * w;
@@ -147,7 +149,6 @@ peak_candidates_kernel(DecodeArgs a) {
         const bool valid = col < ncols;
         const int c = valid ? col / w : 0;
         const int x = valid ? col - c * w : 0;
-        uint32_t kept[kCandRows];
         unsigned posmask = 0;
         if (valid) {
             const uint32_t* t = tkeys + (size_t)c * tplane + x;   // tile row 0 (halo above the slab)
@@ -158,15 +159,13 @@ peak_candidates_kernel(DecodeArgs a) {
             if (has_r) { h_prev = max(h_prev, t[1]); h_cur = max(h_cur, t[w + 1]); }
 #pragma unroll
             for (int r = 0; r < kCandRows; ++r) {
-                kept[r] = 0;
                 if (r < rows) {
                     const uint32_t* nx = t + (r + 2) * w;
                     const uint32_t own_next = nx[0];
                     uint32_t h_next = own_next;
                     if (has_l) h_next = max(h_next, nx[-1]);
                     if (has_r) h_next = max(h_next, nx[1]);
-                    kept[r] = kept_key(own, max(max(h_prev, h_cur), h_next), a.do_nms != 0);
-                    if (kept[r] > kZeroKey) posmask |= 1u << r;
+                    if (kept_key(own, max(max(h_prev, h_cur), h_next), a.do_nms != 0) > kZeroKey) posmask |= 1u << r;
                     h_prev = h_cur; h_cur = h_next; own = own_next;
                 }
             }
@@ -193,12 +192,15 @@ peak_candidates_kernel(DecodeArgs a) {
         }
         __syncthreads();
         size_t at = (size_t)list_base + warp_sums[warp] + incl - cnt;
-#pragma unroll
-        for (int r = 0; r < kCandRows; ++r) {
-            if (posmask & (1u << r)) {
-                const uint32_t lin = (uint32_t)(c * hw + (r0 + r) * w + x);
-                list[at++] = ((unsigned long long)kept[r] << 32) | (unsigned long long)(0xFFFFFFFFu - lin);
-            }
+        // A positive kept cell keeps its own key, except -inf under a larger neighbour (-inf * 0 = NaN).
+        const uint32_t* tcol = tkeys + (size_t)c * tplane + x;
+        while (posmask) {
+            const int r = __ffs(posmask) - 1;
+            posmask &= posmask - 1;
+            const uint32_t own = tcol[(r + 1) * w];
+            const uint32_t key = (a.do_nms && own == kNegInfKey) ? kNanKey : own;
+            const uint32_t lin = (uint32_t)(c * hw + (r0 + r) * w + x);
+            list[at++] = ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - lin);
         }
         __syncthreads();   // warp_sums / list_base are reused by the next column group
     }
