@@ -247,7 +247,7 @@ def run_b200(args):
         fps, times, cores = run_cpu_arm(steps=2, warmup=1, batch=args.batch)
         v = fps * len(times) / sum(times)
         cpu_baseline = {"value": round(v, 2), "unit": "frames/s", "cores": cores, "kind": "port",
-                        "cpu": cpu_model_name(),
+                        "value_per_core": round(v / cores, 2), "cpu": cpu_model_name(),
                         "sample": "%d frames (2 timed passes of %d after 1 warm-up) of the same workload, one process per "
                                   "core, oracle port of the reference (numpy lexsort+unique BEV, torch max_pool2d+topk decode B=1, "
                                   "post_processing)" % (fps * len(times), fps)}
