@@ -1,0 +1,50 @@
+"""BEV throughput on differently distributed sweeps (uniform = the bench workload; the others stress band balance)."""
+import os, sys, importlib
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import sfa_oracle as O
+P = "lidar-image_object-detection_-fpn_resnet-yolov8_b200"
+fast = importlib.import_module(P + ".fast"); geometry = importlib.import_module(P + ".geometry")
+cnf = importlib.import_module(P + ".config.kitti_config")
+dev = torch.device("cuda", 0)
+B, N = 64, 120000
+rng = np.random.default_rng(0)
+b = O.KITTI.boundary
+def uniform():
+    return np.stack([rng.uniform(0, 50, N), rng.uniform(-25, 25, N), rng.uniform(-2.73, 1.27, N), rng.uniform(0, 1, N)], 1)
+def lidar_like():   # range density ~ 1/r (rings of a spinning lidar), azimuth uniform in the front 90 degrees
+    r = np.exp(rng.uniform(np.log(2.0), np.log(70.0), N)); a = rng.uniform(-np.pi / 4, np.pi / 4, N)
+    return np.stack([r * np.cos(a), r * np.sin(a), rng.uniform(-2.73, 1.27, N), rng.uniform(0, 1, N)], 1)
+def near_field():   # 80 % of the points within 10 m
+    x = np.where(rng.uniform(0, 1, N) < 0.8, rng.uniform(0, 10, N), rng.uniform(0, 50, N))
+    return np.stack([x, rng.uniform(-25, 25, N), rng.uniform(-2.73, 1.27, N), rng.uniform(0, 1, N)], 1)
+def scanlines():    # consecutive points are neighbours in space (sorted by azimuth within 64 rings)
+    ring = np.repeat(np.arange(64), N // 64 + 1)[:N]; a = np.tile(np.linspace(-np.pi / 4, np.pi / 4, N // 64 + 1), 64)[:N]
+    r = 3.0 + ring * 0.9 + rng.normal(0, 0.05, N)
+    return np.stack([r * np.cos(a), r * np.sin(a), rng.uniform(-2.73, 1.27, N), rng.uniform(0, 1, N)], 1)
+geom = geometry.from_config(cnf)
+rast = fast.BevRasterizer(geom, max_batch=B, max_points=N, device=dev)
+out = torch.empty((B, 3, 608, 608), device=dev)
+for name, gen in (("uniform (bench)", uniform), ("lidar-like 1/r", lidar_like), ("80% within 10 m", near_field), ("scan lines", scanlines)):
+    pts_np = np.stack([gen() for _ in range(B)]).astype(np.float32)
+    pts = torch.from_numpy(pts_np).to(dev)
+    got = rast.rasterize_uniform(pts, out=out)
+    torch.cuda.synchronize()
+    want = O.make_bev_scatter(pts_np[5], O.KITTI, True, np.float32)
+    assert np.array_equal(got[5].cpu().numpy().view(np.uint32), want.view(np.uint32)), name
+    kept = int(np.count_nonzero((pts_np[5][:, 0] >= 0) & (pts_np[5][:, 0] <= 50) & (np.abs(pts_np[5][:, 1]) <= 25)))
+    torch.cuda._sleep(5_000_000)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20): rast.rasterize_uniform(pts, out=out)
+    e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 20 * 1e3
+    L = importlib.import_module(P + "._lib")
+    with L.profile() as prof:
+        torch.cuda._sleep(5_000_000)
+        for _ in range(5): rast.rasterize_uniform(pts, out=out)
+        torch.cuda.synchronize()
+    print("   ", {k: round(v[1] / 5 * 1e3, 1) for k, v in prof.stats.items()}, "us per 64 frames")
+    print("%-18s kept %6d/%d pts  occupied %6d cells  %7.1f us per 64 frames  (%.2f us/frame)" %
+          (name, kept, N, int(np.count_nonzero(want[2])), us, us / B))
