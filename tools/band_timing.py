@@ -20,11 +20,11 @@ for _ in range(reps): rast.rasterize_uniform(pts, out=out)
 torch.cuda.synchronize()
 buf = (ctypes.c_ulonglong * 16)(); fn(buf, 0)
 names = ["clear+barrier", "records wait + phase1", "phase2", "phase3+fence", "prefetch+store issue", "TMA read-out wait"]
-items = reps * B * 64
+items = reps * B * 128
 tot = sum(buf[:6])
 for k, nme in enumerate(names):
     print("%-24s %8.0f cycles/item  %5.1f%%" % (nme, buf[k] / items, 100.0 * buf[k] / tot))
-print("total per item %.0f cycles; items per CTA %.1f" % (tot / items, B * 64 / 296))
+print("total per item %.0f cycles; items per CTA %.1f" % (tot / items, B * 128 / 592))
 
 bnames = ["offsets + load issue + barrier", "points wait + cells + histogram", "scan + global atomics", "stage", "copy-out issue"]
 tiles = reps * B * ((N + 2047) // 2048)
