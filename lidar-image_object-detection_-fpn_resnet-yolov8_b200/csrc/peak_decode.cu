@@ -38,6 +38,8 @@ namespace {
 constexpr int kCandThreads = 512;
 constexpr int kCandWarps = kCandThreads / 32;
 constexpr int kCandRows = 16;              // rows of a slab
+constexpr int kCapClasses = 8;             // plateau cap: classes a column group may span ...
+constexpr int kCapWords = 16;              // ... and 32-bit words per map row (w <= 512)
 constexpr int kSelThreads = 1024;
 constexpr int kSelSmemItems = 12288;       // candidate words selected from shared memory (96 KB)
 constexpr int kSelUnroll = 4;              // list entries a select thread loads before it processes them
@@ -87,7 +89,9 @@ __global__ void __launch_bounds__(kCandThreads)
 peak_candidates_kernel(DecodeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned int warp_sums[kCandWarps];
-    __shared__ unsigned int list_base;
+    __shared__ unsigned int list_base, grp_min, grp_nmin;
+    __shared__ uint32_t capbits[kCapClasses * kCandRows * kCapWords];   // bitmap of the group's lowest-key cells
+    __shared__ uint32_t caprow[kCapClasses * kCandRows];                // per (class, row): cells before it
     uint32_t* tkeys = reinterpret_cast<uint32_t*>(smem_raw);   // [C][kCandRows + 2][w]
     const int b = blockIdx.y;
     const int C = a.C, h = a.h, w = a.w;
@@ -97,12 +101,15 @@ peak_candidates_kernel(DecodeArgs a) {
     constexpr int trows = kCandRows + 2;
     const int tplane = trows * w;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { grp_min = 0xFFFFFFFFu; grp_nmin = 0; }
+    __syncthreads();   // before any warp's atomicMin on grp_min
 
     // ---- stage slab + halo rows (r0-1 .. r0+rows) as orderable keys ---------------------------------
     // Per class the tile rows that exist in the map are one contiguous run of the NCHW plane, so the
     // copy is linear; rows outside the map get key 0, below every real value (max_pool2d pads with
     // -inf, whose key is 0x007FFFFF).  NaN maps to the largest key, so an integer max propagates it
     // exactly like ATen's max_pool2d does.
+    uint32_t tile_min = 0xFFFFFFFFu;   // lowest key among the tile's in-map cells (see "plateau cap" below)
     {
         const float* hmb = a.hm + (size_t)b * C * hw;
         const int y_lo = r0 - 1;
@@ -123,6 +130,7 @@ peak_candidates_kernel(DecodeArgs a) {
                     const bool sg = a.apply_sigmoid != 0;
                     k = make_uint4(orderable_u32(act(v.x, sg), kNanKey), orderable_u32(act(v.y, sg), kNanKey),
                                    orderable_u32(act(v.z, sg), kNanKey), orderable_u32(act(v.w, sg), kNanKey));
+                    tile_min = min(tile_min, min(min(k.x, k.y), min(k.z, k.w)));
                 }
                 dst[i] = k;
                 t4 += kCandThreads;
@@ -133,12 +141,19 @@ peak_candidates_kernel(DecodeArgs a) {
             for (int c = 0; c < C; ++c) {
                 const float* src = hmb + (size_t)c * hw + (ptrdiff_t)y_lo * w;
                 uint32_t* dst = tkeys + (size_t)c * tplane;
-                for (int i = tid; i < tplane; i += kCandThreads)
-                    dst[i] = (i >= lo && i < hi) ? orderable_u32(act(__ldg(src + i), a.apply_sigmoid != 0), kNanKey) : 0u;
+                for (int i = tid; i < tplane; i += kCandThreads) {
+                    const bool in = i >= lo && i < hi;
+                    const uint32_t k = in ? orderable_u32(act(__ldg(src + i), a.apply_sigmoid != 0), kNanKey) : 0u;
+                    if (in) tile_min = min(tile_min, k);
+                    dst[i] = k;
+                }
             }
         }
     }
+    tile_min = __reduce_min_sync(0xFFFFFFFFu, tile_min);
+    if (lane == 0) atomicMin(&grp_min, tile_min);
     __syncthreads();
+    const uint32_t vmin = grp_min;
 
     // ---- one thread walks one (class, x) column down the slab ---------------------------------------
     const size_t frame_cap = (size_t)C * hw;
@@ -149,7 +164,7 @@ peak_candidates_kernel(DecodeArgs a) {
         const bool valid = col < ncols;
         const int c = valid ? col / w : 0;
         const int x = valid ? col - c * w : 0;
-        unsigned posmask = 0;
+        unsigned posmask = 0, minmask = 0;
         if (valid) {
             const uint32_t* t = tkeys + (size_t)c * tplane + x;   // tile row 0 (halo above the slab)
             const bool has_l = x > 0, has_r = x < w - 1;
@@ -165,11 +180,72 @@ peak_candidates_kernel(DecodeArgs a) {
                     uint32_t h_next = own_next;
                     if (has_l) h_next = max(h_next, nx[-1]);
                     if (has_r) h_next = max(h_next, nx[1]);
-                    if (kept_key(own, max(max(h_prev, h_cur), h_next), a.do_nms != 0) > kZeroKey) posmask |= 1u << r;
+                    const uint32_t kept = kept_key(own, max(max(h_prev, h_cur), h_next), a.do_nms != 0);
+                    if (kept > kZeroKey) posmask |= 1u << r;
+                    if (kept > kZeroKey && kept == vmin) minmask |= 1u << r;
                     h_prev = h_cur; h_cur = h_next; own = own_next;
                 }
             }
         }
+        // ---- plateau cap ---------------------------------------------------------------------------
+        // Among cells with EQUAL keys the top-K takes the lowest linear indices, so of the cells of this
+        // column group that share one key only the K lowest-index ones can ever be selected.  Applied to
+        // the tile's LOWEST key (found for free while the tile is staged) — the floor a clamped sigmoid
+        // plateaus at, or a constant map — this keeps such maps from listing every cell (69 k words per
+        // frame) without changing any result; where the lowest cell is no kept peak (any ordinary map)
+        // it costs one warp reduction and one barrier.
+        const uint32_t* tcol = tkeys + (size_t)c * tplane + x;
+        auto key_at = [&](int r) -> uint32_t {   // a positive kept cell keeps its own key, except -inf under a
+            const uint32_t own = tcol[(r + 1) * w];   // larger neighbour (-inf * 0 = NaN)
+            return (a.do_nms && own == kNegInfKey) ? kNanKey : own;
+        };
+        {
+            const unsigned wn = __reduce_add_sync(0xFFFFFFFFu, (unsigned)__popc(minmask));
+            if (lane == 0 && wn) atomicAdd(&grp_nmin, wn);
+        }
+        __syncthreads();
+        const int c_first = col0 / w;
+        const int n_cls = min(ncols - 1, col0 + kCandThreads - 1) / w - c_first + 1;
+        const int words = (w + 31) >> 5;
+        if (grp_nmin > (unsigned)a.K && n_cls <= kCapClasses && words <= kCapWords) {   // block-uniform
+            const int n_rows = n_cls * kCandRows;
+            for (int i = tid; i < n_rows * kCapWords; i += kCandThreads) capbits[i] = 0;
+            __syncthreads();
+            const int row0 = (c - c_first) * kCandRows;
+            for (unsigned m = minmask; m; m &= m - 1)
+                atomicOr(&capbits[(row0 + __ffs(m) - 1) * kCapWords + (x >> 5)], 1u << (x & 31));
+            __syncthreads();
+            if (tid < n_rows) {
+                unsigned tot = 0;
+                for (int j = 0; j < words; ++j) tot += __popc(capbits[tid * kCapWords + j]);
+                caprow[tid] = tot;
+            }
+            __syncthreads();
+            if (warp == 0) {   // exclusive scan over the (<= 128) rows in (class, row) order = linear-index order
+                constexpr int per = kCapClasses * kCandRows / 32;
+                unsigned v[per], run = 0;
+#pragma unroll
+                for (int q = 0; q < per; ++q) { v[q] = lane * per + q < n_rows ? caprow[lane * per + q] : 0u; run += v[q]; }
+                unsigned incl = run;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                unsigned at = incl - run;
+#pragma unroll
+                for (int q = 0; q < per; ++q) { if (lane * per + q < n_rows) caprow[lane * per + q] = at; at += v[q]; }
+            }
+            __syncthreads();
+            for (unsigned m = minmask; m; m &= m - 1) {
+                const int r = __ffs(m) - 1;
+                const uint32_t* rowbits = capbits + (row0 + r) * kCapWords;
+                unsigned rank = caprow[row0 + r] + __popc(rowbits[x >> 5] & ((1u << (x & 31)) - 1u));
+                for (int j = 0; j < (x >> 5); ++j) rank += __popc(rowbits[j]);
+                if (rank >= (unsigned)a.K) posmask &= ~(1u << r);   // K lower-index cells of the same key exist
+            }
+        }
+
         // exclusive scan of the per-thread counts; one global atomicAdd reserves the CTA's run
         const unsigned cnt = (unsigned)__popc(posmask);
         unsigned incl = cnt;
@@ -192,17 +268,14 @@ peak_candidates_kernel(DecodeArgs a) {
         }
         __syncthreads();
         size_t at = (size_t)list_base + warp_sums[warp] + incl - cnt;
-        // A positive kept cell keeps its own key, except -inf under a larger neighbour (-inf * 0 = NaN).
-        const uint32_t* tcol = tkeys + (size_t)c * tplane + x;
         while (posmask) {
             const int r = __ffs(posmask) - 1;
             posmask &= posmask - 1;
-            const uint32_t own = tcol[(r + 1) * w];
-            const uint32_t key = (a.do_nms && own == kNegInfKey) ? kNanKey : own;
             const uint32_t lin = (uint32_t)(c * hw + (r0 + r) * w + x);
-            list[at++] = ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - lin);
+            list[at++] = ((unsigned long long)key_at(r) << 32) | (unsigned long long)(0xFFFFFFFFu - lin);
         }
-        __syncthreads();   // warp_sums / list_base are reused by the next column group
+        if (tid == 0) grp_nmin = 0;
+        __syncthreads();   // warp_sums / list_base / grp_nmin are reused by the next column group
     }
 }
 

@@ -288,3 +288,31 @@ def test_convert_det_to_real_values_device_and_host(cuda_device):
         r, c, k = real[i].cpu().numpy(), cls[i].cpu().numpy(), keep[i].cpu().numpy()
         got = np.concatenate([r[(c == j) & k] for j in range(3)], 0)
         np.testing.assert_allclose(got.astype(np.float64), want, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("C,h,w,K", [(3, 152, 152, 50), (3, 200, 200, 128), (1, 40, 600, 30), (5, 33, 70, 17), (2, 64, 512, 50)])
+def test_decode_plateau_maps_exact_tie_order(cuda_device, C, h, w, K):
+    """Clamped-sigmoid style maps: a floor plateau everywhere (every plateau cell is a kept peak), a few cells above it —
+    fewer than K, so the top K must be completed with the LOWEST-index plateau cells — plus a second, higher plateau.
+    The candidate kernel lists only the K lowest-index floor cells per column group (the rest can never be selected);
+    the result must equal the exact (score desc, class asc, index asc) order.  Shapes cover one / several column
+    groups, rows wider than the cap bitmap (cap off), and K up to 128."""
+    g = torch.Generator().manual_seed(C * 1000 + w)
+    B = 3
+    hm = torch.full((B, C, h, w), 1e-4)
+    n_peaks = max(1, K // 3)
+    for b in range(B):
+        idx = torch.randperm(C * h * w, generator=g)[:n_peaks]
+        hm[b].view(-1)[idx] = torch.rand(n_peaks, generator=g) * 0.5 + 0.3
+    hm[:, C - 1, h // 2:h // 2 + 3, 2:7] = 0.25          # a second plateau above the floor
+    _, off, d, z, dim = O.synth_heads(5, B=B, C=C, h=h, w=w)
+    got = _ev().decode(*_cuda((hm, off, d, z, dim), cuda_device), K=K).cpu().numpy()
+    nms = O._nms(hm.clone())
+    for b in range(B):
+        flat = nms[b].reshape(-1).numpy()
+        order = np.lexsort((np.arange(flat.size), -flat.astype(np.float64)))[:K]
+        assert np.array_equal(got[b, :, 0], flat[order])
+        assert np.array_equal(got[b, :, 9].astype(np.int64), order // (h * w))
+        sp = order % (h * w)
+        assert np.array_equal(got[b, :, 1], (sp % w).astype(np.float32) + off[b, 0].reshape(-1).numpy()[sp])
+        assert np.array_equal(got[b, :, 2], (sp // w).astype(np.float32) + off[b, 1].reshape(-1).numpy()[sp])
