@@ -316,3 +316,41 @@ def test_decode_plateau_maps_exact_tie_order(cuda_device, C, h, w, K):
         sp = order % (h * w)
         assert np.array_equal(got[b, :, 1], (sp % w).astype(np.float32) + off[b, 0].reshape(-1).numpy()[sp])
         assert np.array_equal(got[b, :, 2], (sp // w).astype(np.float32) + off[b, 1].reshape(-1).numpy()[sp])
+
+
+def test_error_paths_report_status_and_message(cuda_device):
+    """The C ABI never throws and never corrupts: bad calls return a negative status with a message."""
+    import ctypes
+    L = pkg("_lib")
+    lib = L.load()
+    fast = pkg("fast")
+    heads = _cuda(O.synth_heads(1, B=2, tie_free=True), cuda_device)
+    with pytest.raises(RuntimeError, match="K=129"):
+        fast.decode_device(*heads, K=129)                      # K > 128 is not supported
+    det = torch.empty((2, 50, 10), device=cuda_device)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(cuda_device).cuda_stream)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    small = torch.empty(1024, dtype=torch.uint8, device=cuda_device)
+    ws = small.data_ptr() + (-small.data_ptr()) % 256
+    rc = lib.sfa_decode(p(heads[0]), p(heads[1]), p(heads[2]), p(heads[3]), p(heads[4]), 2, 3, 152, 152, 50, p(det), None, 0,
+                        ctypes.c_void_p(ws), 512, stream)
+    assert rc == -2 and "workspace too small" in L.last_error()   # SFA_ERR_WORKSPACE_TOO_SMALL
+    rc = lib.sfa_decode(p(heads[0]), p(heads[1]), p(heads[2]), p(heads[3]), p(heads[4]), 2, 3, 152, 152, 50, p(det), None, 0,
+                        ctypes.c_void_p(ws + 4), 1 << 30, stream)
+    assert rc == -1 and "aligned" in L.last_error()
+    # BEV: workspace sized for fewer points than the call declares
+    geom = pkg("geometry").from_config(pkg("config.kitti_config"))
+    rast = fast.BevRasterizer(geom, max_batch=2, max_points=1000, device=cuda_device)
+    pts = torch.zeros((2, 5000, 4), device=cuda_device)
+    with pytest.raises(ValueError):
+        rast.rasterize_uniform(pts)
+    lut = torch.from_numpy(geom.lut32.copy()).to(cuda_device)
+    out = torch.empty((2, 3, 608, 608), device=cuda_device)
+    rc = lib.sfa_bev_rasterize(p(pts), None, 2, 5000, ctypes.byref(geom.params), p(lut), p(out), None,
+                               ctypes.c_void_p(rast._ws_ptr), rast._ws_bytes, stream)
+    assert rc == -2 and "workspace too small" in L.last_error()
+    torch.cuda.synchronize()
+    # and the library is still healthy afterwards
+    got = fast.decode_device(*heads, K=50).cpu().numpy()
+    want = O.decode(*[t.cpu().clone() for t in heads], K=50).numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
