@@ -377,3 +377,33 @@ def test_exact_division_matches_div_rn_over_every_float_in_range(cuda_device, d)
         pkg("_lib").check(lib.sfa_selftest_division(d32, first, count, ctypes.c_void_p(bad.data_ptr()), stream))
     torch.cuda.synchronize()
     assert int(bad.item()) == 0
+
+
+def test_bev_random_geometries(cuda_device):
+    """40 random map geometries (size, cell size, boundary placement incl. negative x / asymmetric y, max height) x
+    random sweeps that partly leave the boundary: exercises band plans with tiny / partial last bands, the
+    proven-in-range fast path vs the per-point range test, the exact-division and the true-division height paths."""
+    rng = np.random.default_rng(2024)
+    for trial in range(40):
+        H = int(rng.choice([8, 20, 64, 100, 152, 304, 400, 608, 700]))
+        W = int(rng.choice([8, 36, 64, 152, 304, 608, 640]))
+        if (H * W) % 4:
+            W += 4 - (W % 4) if (H % 4) else 0
+        size_x = float(rng.choice([10.0, 25.0, 50.0, 80.0]))
+        d = size_x / H
+        min_x = float(rng.choice([0.0, 0.0, -size_x, -size_x / 2, 3.0]))
+        half_y = d * W / 2 * float(rng.choice([1.0, 1.0, 0.7]))      # 0.7: the filter keeps y well inside the map
+        min_z, max_z = float(rng.choice([-2.73, -3.0, -1.0])), float(rng.choice([1.27, 5.0, 2.0]))
+        boundary = {"minX": min_x, "maxX": min_x + size_x, "minY": -half_y, "maxY": half_y, "minZ": min_z, "maxZ": max_z}
+        if min_x < 0 and -min_x / d > H:       # negative rows would wrap beyond the map: the reference raises there
+            continue
+        g = O.Geometry(boundary=boundary, BEV_HEIGHT=H, BEV_WIDTH=W, DISCRETIZATION=d)
+        n = int(rng.integers(1, 20000))
+        sweep = O.synth_sweep(int(rng.integers(0, 1 << 30)), n, g, str(rng.choice(["uniform", "outside", "zties", "bounds", "gridaligned"])))
+        try:
+            want = O.make_bev_scatter(sweep, g, True, np.float32)
+        except IndexError:
+            continue                            # the reference would raise for this geometry
+        got, rast = _run_batch(cuda_device, [sweep], g)
+        _assert_bit_exact(got[0], want, "trial %d H=%d W=%d d=%g minX=%g" % (trial, H, W, d, min_x))
+        assert rast.out_of_map_points() == 0
