@@ -59,6 +59,8 @@ PROTOTYPES = {
                                   c_void_p, i32, c_void_p, sz, c_void_p]),
     "sfa_post_process": (ctypes.c_int, [c_void_p, i32, i32, i32, f32, f32, f32, f32, f32, f32, f32, f32, f32, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sfa_project_boxes": (ctypes.c_int, [c_void_p, i32, c_void_p, i32, i32, c_void_p, i32, i32, i32, ctypes.c_double,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sfa_pipeline_create": (c_void_p, [i32, i32, i64, ctypes.POINTER(SfaBevParams), c_void_p, i32, i32, i32, i32]),
     "sfa_pipeline_destroy": (None, [c_void_p]),
     "sfa_pipeline_bev_host": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, i32, c_void_p, c_void_p]),

@@ -220,6 +220,62 @@ def post_process_dense(detections, num_classes=3, down_ratio=4, peak_thresh=0.2,
     return res if real is None else res + (real,)
 
 
+def pack_calibration(V2C, R0, P2, device=None):
+    """Calibration matrices (data_process/kitti_data_utils.py:127-139: float32 V2C [3,4], R0 [3,3],
+    P2 [3,4]; leading batch dimensions allowed, 4x4 homogeneous forms are cut down) -> float64
+    [..., 33] in the layout sfa_project_boxes reads."""
+    def cut(m, r, c):
+        m = np.asarray(m, dtype=np.float64)
+        return m[..., :r, :c].reshape(m.shape[:-2] + (r * c,))
+    packed = np.concatenate([cut(V2C, 3, 4), cut(R0, 3, 3), cut(P2, 3, 4)], axis=-1)
+    t = torch.from_numpy(np.ascontiguousarray(packed))
+    return t if device is None else t.to(device)
+
+
+def project_boxes_dense(real, calib, img_shape, keep=None, min_confidence=0.3, want_cam=False, want_float=False,
+                        out=None):
+    """Dense lidar_to_camera_box + convert_sfa3d_to_2d_boxes (data_process/transformation.py:99-107,
+    test6.py:129-187) on the device.  real: CUDA [B,K,8] float32/float64 rows as produced by
+    post_process_dense(real=True); calib: pack_calibration(...) on the device, [33] or [B,33];
+    img_shape = (height, width).  Returns (box [B,K,4] i32 = x, y, w, h; valid [B,K] bool) and, if
+    requested, cam [B,K,7] f64 and the clipped float bounds [B,K,4] f64.  With
+    `out=(box, valid_u8)` nothing is allocated."""
+    lib = _lib.load()
+    _require_cuda(real, "real")
+    if real.dtype not in (torch.float32, torch.float64):
+        real = real.float()
+    real = real.contiguous()
+    if real.dim() != 3 or real.shape[2] != 8:
+        raise ValueError("real must be [B, K, 8]")
+    B, K = real.shape[0], real.shape[1]
+    _require_cuda(calib, "calib")
+    if calib.dtype != torch.float64 or calib.shape[-1] != 33 or not calib.is_contiguous():
+        raise ValueError("calib must be a contiguous float64 [33] or [B,33] tensor (see pack_calibration)")
+    per_frame = calib.dim() == 2
+    if per_frame and calib.shape[0] != B:
+        raise ValueError("calib has %d rows for %d frames" % (calib.shape[0], B))
+    dev = real.device
+    if out is None:
+        box = torch.empty((B, K, 4), dtype=torch.int32, device=dev)
+        valid = torch.empty((B, K), dtype=torch.uint8, device=dev)
+    else:
+        box, valid = out
+    cam = torch.empty((B, K, 7), dtype=torch.float64, device=dev) if want_cam else None
+    box_f = torch.empty((B, K, 4), dtype=torch.float64, device=dev) if want_float else None
+    if keep is not None:
+        keep = keep.to(torch.uint8).contiguous()
+    with torch.cuda.device(dev):
+        _lib.check(lib.sfa_project_boxes(_ptr(real), int(real.dtype == torch.float64), _ptr(keep), B, K, _ptr(calib),
+                                         int(per_frame), int(img_shape[0]), int(img_shape[1]), float(min_confidence),
+                                         _ptr(cam), _ptr(box_f), _ptr(box), _ptr(valid), _stream_ptr(dev)))
+    res = (box, valid.bool() if out is None else valid)
+    if want_cam:
+        res += (cam,)
+    if want_float:
+        res += (box_f,)
+    return res
+
+
 class HostPipeline:
     """Host-buffer entry points (sfa_pipeline_*): numpy / CPU tensors in, numpy out, with chunked,
     overlapped H2D -> kernels -> D2H inside the library.  This is what the drop-in makeBEVMap /

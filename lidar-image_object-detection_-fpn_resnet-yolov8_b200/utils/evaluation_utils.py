@@ -1,7 +1,8 @@
 """Drop-in for the hot-path functions of the reference's utils/evaluation_utils.py:
 `_nms` (:21-26), `_topk` (:47-62), `decode` (:77-105), `post_processing` (:112-163) and
 `convert_det_to_real_values` (:177-193) — same names, arguments, return types and error behaviour,
-computed by libsfa_b200.so on the B200.  `draw_predictions` (cv2) is out of scope.
+computed by libsfa_b200.so on the B200 — plus `convert_sfa3d_to_2d_boxes`, which the reference keeps
+inside its fusion scripts (test6.py:129-187).  `draw_predictions` (cv2) is out of scope.
 
 CUDA tensors are processed in place on the current stream and the result stays on the device; CPU
 tensors (most reference scripts pin the model to the CPU, test.py:50) go through the library's
@@ -153,3 +154,30 @@ def convert_det_to_real_values(detections, num_classes=3):
         r[:, 7] = -d[:, 7]
         out.append(r)
     return np.concatenate(out, 0) if out else np.array([])
+
+
+def convert_sfa3d_to_2d_boxes(sfa_detections, calib, img_shape, min_confidence=0.3):
+    """One sample's post_processing dict -> (image boxes [[x, y, w, h], ...], confidences) through the
+    calibration object's V2C / R0 / P2 — test6.py:129-187 (test4.py:128-186; msac.py / slam.py:130-201
+    pass the matrices in a dict and use min_confidence=0.2, both accepted here).  Literal behaviour
+    kept: the value tested against min_confidence and returned as "confidence" is column 0 of the
+    real-value row, which is the class id (evaluation_utils.py:191).  The batched device form is
+    fast.project_boxes_dense."""
+    from .. import fast
+    boxes_2d, confidences = [], []
+    if len(sfa_detections) == 0:
+        return boxes_2d, confidences
+    kitti_dets = np.asarray(convert_det_to_real_values(sfa_detections), dtype=np.float64).reshape(-1, 8)
+    if kitti_dets.shape[0] == 0:
+        return boxes_2d, confidences
+    _need_cuda()
+    get = (lambda k: calib[k]) if isinstance(calib, dict) else (lambda k: getattr(calib, k))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    packed = fast.pack_calibration(get("V2C"), get("R0"), get("P2"), device=dev)
+    box, valid = fast.project_boxes_dense(torch.from_numpy(kitti_dets[None]).to(dev), packed, img_shape,
+                                          min_confidence=min_confidence)
+    box, valid = box[0].cpu().numpy(), valid[0].cpu().numpy()
+    for i in np.nonzero(valid)[0]:
+        boxes_2d.append([int(v) for v in box[i]])
+        confidences.append(kitti_dets[i, 0])
+    return boxes_2d, confidences

@@ -308,6 +308,92 @@ def convert_det_to_real_values(detections, num_classes=3, geom: Geometry = KITTI
     return np.array(out)
 
 
+# ----------------------------------------------------------------------------- lidar boxes -> camera frame -> image
+def lidar_to_camera(x, y, z, V2C, R0):
+    """data_process/transformation.py:50-60 with explicit calibration (V2C 3x4, R0 3x3)."""
+    p = np.array([x, y, z, 1])
+    p = np.matmul(V2C, p)
+    p = np.matmul(R0, p)
+    return tuple(p[0:3])
+
+
+def lidar_to_camera_box(boxes, V2C, R0, P2=None):
+    """data_process/transformation.py:99-107: (N,7) x,y,z,h,w,l,rz -> x,y,z (rect camera frame),h,w,l,ry."""
+    ret = []
+    for box in boxes:
+        x, y, z, h, w, l, rz = box
+        (x, y, z), ry = lidar_to_camera(x, y, z, V2C, R0), -rz - np.pi / 2
+        ret.append([x, y, z, h, w, l, ry])
+    return np.array(ret).reshape(-1, 7)
+
+
+def project_box_to_image(box_3d_cam, P2, img_shape):
+    """test6.py:147-185 (same body in test4.py:146-184, msac.py:161-199, slam.py:161-199): the 8
+    corners of the camera-frame box through P2 -> axis-aligned image box, clipped with Python's
+    max()/min() (a NaN bound falls back to the image border).  Returns (min_x, min_y, max_x, max_y)
+    as floats and whether the reference would emit the box."""
+    x, y, z, h, w, l, ry = box_3d_cam
+    corners_3d = np.array([
+        [-l / 2, -l / 2, l / 2, l / 2, -l / 2, -l / 2, l / 2, l / 2],
+        [0, 0, 0, 0, -h, -h, -h, -h],
+        [-w / 2, w / 2, w / 2, -w / 2, -w / 2, w / 2, w / 2, -w / 2]])
+    R = np.array([[np.cos(ry), 0, np.sin(ry)], [0, 1, 0], [-np.sin(ry), 0, np.cos(ry)]])
+    corners_3d = np.dot(R, corners_3d)
+    corners_3d[0, :] += x
+    corners_3d[1, :] += y
+    corners_3d[2, :] += z
+    with np.errstate(all="ignore"):
+        corners_2d = P2.dot(np.vstack((corners_3d, np.ones((1, 8)))))
+        corners_2d = corners_2d[:2] / corners_2d[2]
+    min_x, max_x = np.min(corners_2d[0]), np.max(corners_2d[0])
+    min_y, max_y = np.min(corners_2d[1]), np.max(corners_2d[1])
+    min_x = max(0, min_x)
+    min_y = max(0, min_y)
+    max_x = min(img_shape[1], max_x)
+    max_y = min(img_shape[0], max_y)
+    return (float(min_x), float(min_y), float(max_x), float(max_y)), bool(max_x > min_x and max_y > min_y)
+
+
+def convert_sfa3d_to_2d_boxes(sfa_detections, V2C, R0, P2, img_shape, min_confidence=0.3, geom: Geometry = KITTI):
+    """test6.py:129-187.  Literal behaviour kept: `confidence` is column 0 of the real-value row, which
+    convert_det_to_real_values fills with the CLASS ID (evaluation_utils.py:191), so class 0 is always
+    skipped and the returned confidences are class ids.  min_confidence is 0.3 in test4/test6 and 0.2
+    in msac/slam."""
+    boxes_2d, confidences = [], []
+    if len(sfa_detections) > 0:
+        for detection in convert_det_to_real_values(sfa_detections, geom=geom):
+            confidence = detection[0]
+            if confidence < min_confidence:
+                continue
+            cam = lidar_to_camera_box(detection[1:].reshape(1, -1), V2C, R0, P2)[0]
+            (min_x, min_y, max_x, max_y), ok = project_box_to_image(cam, P2, img_shape)
+            if ok:
+                boxes_2d.append([int(min_x), int(min_y), int(max_x - min_x), int(max_y - min_y)])
+                confidences.append(confidence)
+    return boxes_2d, confidences
+
+
+def synth_calibration(seed=0):
+    """A KITTI-like calibration (float32, as Calibration.read_calib_file parses it,
+    data_process/kitti_data_utils.py:149-170): the dataset-average matrices of
+    config/kitti_config.py:64-83 with a small seeded perturbation."""
+    rng = np.random.default_rng(seed)
+    V2C = np.array([[7.49916597e-03, -9.99971248e-01, -8.65110297e-04, -6.71807577e-03],
+                    [1.18652889e-02, 9.54520517e-04, -9.99910318e-01, -7.33152811e-02],
+                    [9.99882833e-01, 7.49141178e-03, 1.18719929e-02, -2.78557062e-01]])
+    R0 = np.array([[0.99992475, 0.00975976, -0.00734152],
+                   [-0.0097913, 0.99994262, -0.00430371],
+                   [0.00729911, 0.0043753, 0.99996319]])
+    P2 = np.array([[719.787081, 0., 608.463003, 44.9538775],
+                   [0., 719.787081, 174.545111, 0.1066855],
+                   [0., 0., 1., 3.0106472e-03]])
+    if seed:
+        V2C = V2C + rng.normal(0, 1e-3, V2C.shape)
+        R0 = R0 + rng.normal(0, 1e-4, R0.shape)
+        P2 = P2 * (1 + rng.normal(0, 1e-2)) * np.array([[1, 0, 1, 1], [0, 1, 1, 1], [0, 0, 1, 1]])
+    return V2C.astype(np.float32), R0.astype(np.float32), P2.astype(np.float32)
+
+
 # ----------------------------------------------------------------------------- tie-insensitive decode comparator
 def canonical_detections(det):
     """torch.topk's order among EQUAL scores is implementation-defined (SURVEY.md §7 "top-K ties"),

@@ -12,6 +12,9 @@ seeded synthetic inputs, outputs stored here.  Nothing reads /root/reference at 
                      that the tests regenerate from the seed
   decode_small.npz   explicit heads + reference _nms/_topk/decode/post_processing/convert outputs
   decode_hashes.json sha256 pins at the full 152x152 head size, B=4, K=50
+  projection_small.npz  post-processed detections + calibration -> the reference's lidar_to_camera_box
+                     rows and convert_sfa3d_to_2d_boxes image boxes (test6.py:129-187), incl. boxes
+                     behind the camera, straddling the image plane, outside the image and NaN rows
 """
 import hashlib
 import json
@@ -156,13 +159,70 @@ def make_decode(ns):
     return len(cases), len(hashes)
 
 
+class _Calib:
+    def __init__(self, V2C, R0, P2):
+        self.V2C, self.R0, self.P2 = V2C, R0, P2
+
+
+def projection_cases():
+    """(name, per-class detection dict in post_processing's format, calibration seed, image shape)."""
+    cases = []
+    for s in range(3):
+        heads = O.synth_heads(500 + s, B=1, tie_free=True)
+        det = O.decode(*heads, K=50).numpy().astype(np.float32)
+        cases.append(("decode%d" % s, O.post_processing(det, peak_thresh=0.2)[0], s, (375, 1242)))
+    f = np.float32
+    # score, x_px, y_px, z, h, w_px, l_px, yaw   (x_px across y, y_px along x: evaluation_utils.py:184-185)
+    rows = np.array([
+        [0.9, 304.0, 243.2, 1.0, 1.5, 20.0, 48.0, 0.3],      # 20 m ahead, centred
+        [0.9, 304.0, 3.0, 1.0, 1.5, 20.0, 48.0, 1.2],        # straddles the image plane (depth changes sign)
+        [0.9, 10.0, 12.0, 1.0, 1.5, 20.0, 48.0, -2.0],       # far left, mostly outside the image
+        [0.9, 600.0, 30.0, 1.0, 1.5, 20.0, 48.0, 0.0],       # far right, outside the image
+        [0.9, 304.0, 600.0, 2.0, 3.0, 30.0, 120.0, 3.1],     # 49 m ahead, a few pixels
+        [0.9, 304.0, 243.2, np.nan, 1.5, 20.0, 48.0, 0.3],   # NaN height -> Python max/min fall back to the border
+        [0.9, 304.0, 100.0, 1.0, 0.0, 0.0, 0.0, 0.0],        # degenerate box: zero area, rejected
+        [0.9, 304.0, 120.0, 30.0, 1.5, 20.0, 48.0, 0.5],     # above the image
+    ], dtype=f)
+    cases.append(("crafted", {0: rows[:2].copy(), 1: rows.copy(), 2: rows[::-1].copy()}, 7, (375, 1242)))
+    cases.append(("empty", {0: np.zeros((0, 8), f), 1: np.zeros((0, 8), f), 2: np.zeros((0, 8), f)}, 1, (375, 1242)))
+    cases.append(("small_image", {0: rows[:1].copy(), 1: rows[:5].copy(), 2: rows[2:6].copy()}, 2, (128, 416)))
+    return cases
+
+
+def make_projection(ns):
+    small = {}
+    cases = projection_cases()
+    for name, dets, cseed, shape in cases:
+        V2C, R0, P2 = O.synth_calibration(cseed)
+        for j in range(3):
+            small["%s_det%d" % (name, j)] = np.asarray(dets[j], np.float32).reshape(-1, 8)
+        small[name + "_V2C"], small[name + "_R0"], small[name + "_P2"] = V2C, R0, P2
+        small[name + "_shape"] = np.array(shape)
+        real = np.asarray(ns.convert_det_to_real_values(dets), np.float64).reshape(-1, 8)
+        small[name + "_real"] = real
+        small[name + "_cam"] = (ns.lidar_to_camera_box(real[:, 1:], V2C, R0, P2) if len(real)
+                                else np.zeros((0, 7)))
+        with np.errstate(all="ignore"):
+            boxes, conf = ns.convert_sfa3d_to_2d_boxes(dets, _Calib(V2C, R0, P2), shape)
+        small[name + "_boxes"] = np.asarray(boxes, np.int64).reshape(-1, 4)
+        small[name + "_conf"] = np.asarray(conf, np.float64)
+    small["names"] = np.array([c[0] for c in cases])
+    np.savez_compressed(os.path.join(HERE, "projection_small.npz"), **small)
+    return len(cases)
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference not present; fixtures can only be regenerated in the build container")
     torch.set_num_threads(1)
     ns = ref_loader.load()
-    print("bev: %d small cases, %d hashed" % make_bev(ns))
-    print("decode: %d small cases, %d hashed" % make_decode(ns))
+    only = sys.argv[1:]
+    if not only or "bev" in only:
+        print("bev: %d small cases, %d hashed" % make_bev(ns))
+    if not only or "decode" in only:
+        print("decode: %d small cases, %d hashed" % make_decode(ns))
+    if not only or "projection" in only:
+        print("projection: %d cases" % make_projection(ns))
 
 
 if __name__ == "__main__":

@@ -44,6 +44,22 @@ def _virtual_sfa_root():
 _cache = {}
 
 
+def _script_function(script, name, env):
+    """The reference keeps some steps inside its top-level scripts (test6.py imports ultralytics,
+    open3d ... at module level, which are absent here): compile just the named function's own,
+    unmodified source out of the script and bind the reference functions it calls."""
+    import ast
+    import warnings
+    path = os.path.join(REFERENCE_ROOT, script)
+    with open(path) as f, warnings.catch_warnings():
+        warnings.simplefilter("ignore", SyntaxWarning)
+        tree = ast.parse(f.read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == name][0]
+    env = dict(env)
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), env)
+    return env[name]
+
+
 def load():
     """Returns a namespace with the reference's own functions (unmodified code objects)."""
     if _cache:
@@ -61,6 +77,7 @@ def load():
         dat = importlib.import_module("data_process.kitti_data_utils")
         evl = importlib.import_module("utils.evaluation_utils")
         tch = importlib.import_module("utils.torch_utils")
+        trf = importlib.import_module("data_process.transformation")
         spec = importlib.util.spec_from_file_location(
             "ref_evaluation_utils_pristine", os.path.join(REFERENCE_ROOT, "utils", "evaluation_utils copy.py"))
         pristine = importlib.util.module_from_spec(spec)
@@ -91,6 +108,11 @@ def load():
     ns.post_processing_live = post_processing_live
     ns.post_processing_pristine = post_processing_pristine
     ns.convert_det_to_real_values = evl.convert_det_to_real_values
+    ns.lidar_to_camera_box = trf.lidar_to_camera_box
+    ns.convert_sfa3d_to_2d_boxes = _script_function(
+        "test6.py", "convert_sfa3d_to_2d_boxes",
+        {"np": __import__("numpy"), "convert_det_to_real_values": evl.convert_det_to_real_values,
+         "lidar_to_camera_box": trf.lidar_to_camera_box})
     _cache["ns"] = ns
     return ns
 

@@ -148,3 +148,27 @@ def test_canonical_detections_orders_ties():
     d[0, :, 9] = [0, 2, 1, 0]
     c = O.canonical_detections(d)
     assert list(c[0, :, 9]) == [0, 1, 2, 0]
+
+
+# ----------------------------------------------------------------------------- camera-frame boxes + image projection
+def test_projection_oracle_against_reference_fixture():
+    """oracle lidar_to_camera_box / convert_sfa3d_to_2d_boxes vs what the reference's own functions
+    (data_process/transformation.py:99-107, test6.py:129-187) returned for the committed cases."""
+    z = np.load(os.path.join(GOLD, "projection_small.npz"))
+    names = [str(n) for n in z["names"]]
+    assert names == ["decode0", "decode1", "decode2", "crafted", "empty", "small_image"]
+    total = 0
+    for n in names:
+        dets = {j: z["%s_det%d" % (n, j)] for j in range(3)}
+        V2C, R0, P2 = z[n + "_V2C"], z[n + "_R0"], z[n + "_P2"]
+        assert V2C.dtype == np.float32 and R0.dtype == np.float32 and P2.dtype == np.float32
+        real = np.asarray(O.convert_det_to_real_values(dets), np.float64).reshape(-1, 8)
+        assert np.array_equal(real, z[n + "_real"], equal_nan=True)
+        cam = O.lidar_to_camera_box(real[:, 1:], V2C, R0, P2) if len(real) else np.zeros((0, 7))
+        np.testing.assert_allclose(cam, z[n + "_cam"], rtol=1e-13, atol=1e-13, equal_nan=True)
+        boxes, conf = O.convert_sfa3d_to_2d_boxes(dets, V2C, R0, P2, tuple(z[n + "_shape"]))
+        assert np.array_equal(np.asarray(boxes, np.int64).reshape(-1, 4), z[n + "_boxes"]), n
+        assert np.array_equal(np.asarray(conf, np.float64), z[n + "_conf"]), n
+        assert all(c >= 1 for c in conf)        # class 0 never passes: "confidence" is the class id
+        total += len(boxes)
+    assert total > 80

@@ -64,3 +64,24 @@ def test_decode_oracle_equals_reference(ns, seed, tie_free):
 def test_sigmoid_matches(ns):
     x = torch.randn(4, 3, 16, 16, generator=torch.Generator().manual_seed(0))
     assert torch.equal(ns._sigmoid(x.clone()), O._sigmoid(x.clone()))
+
+
+class _Calib:
+    def __init__(self, V2C, R0, P2):
+        self.V2C, self.R0, self.P2 = V2C, R0, P2
+
+
+@pytest.mark.parametrize("seed", [21, 22])
+def test_projection_oracle_equals_reference(ns, seed):
+    """lidar_to_camera_box (data_process/transformation.py:99-107) and convert_sfa3d_to_2d_boxes
+    (test6.py:129-187, compiled out of the script by ref_loader) on decoded detections."""
+    heads = O.synth_heads(seed, B=2, tie_free=True)
+    det = O.decode(*heads, K=50).numpy().astype(np.float32)
+    V2C, R0, P2 = O.synth_calibration(seed)
+    for sample in O.post_processing(det, peak_thresh=0.2):
+        real = np.asarray(ns.convert_det_to_real_values(sample), np.float64).reshape(-1, 8)
+        assert np.array_equal(ns.lidar_to_camera_box(real[:, 1:], V2C, R0, P2),
+                              O.lidar_to_camera_box(real[:, 1:], V2C, R0, P2))
+        want = ns.convert_sfa3d_to_2d_boxes(sample, _Calib(V2C, R0, P2), (375, 1242))
+        assert want == O.convert_sfa3d_to_2d_boxes(sample, V2C, R0, P2, (375, 1242))
+        assert len(want[0]) > 5
