@@ -22,6 +22,12 @@ class SfaBevParams(ctypes.Structure):
 BEV_AUTO, BEV_TILED, BEV_GLOBAL_ATOMIC = 0, 1, 2   # enum SfaBevAlgorithm
 
 
+class SfaBvParams(ctypes.Structure):
+    """struct SfaBvParams of include/sfa_b200.h (makeBVFeature geometry)."""
+    _fields_ = [("min_x", f32), ("max_x", f32), ("min_y", f32), ("max_y", f32), ("min_z", f32), ("max_z", f32),
+                ("discretization", f32), ("height_range", f32), ("height", i32), ("width", i32), ("point_floats", i32)]
+
+
 class SfaKernelStat(ctypes.Structure):
     """struct SfaKernelStat of include/sfa_b200.h."""
     _fields_ = [("name", ctypes.c_char * 40), ("launches", ctypes.c_uint64), ("total_ms", ctypes.c_double)]
@@ -59,6 +65,9 @@ PROTOTYPES = {
                                   c_void_p, i32, c_void_p, sz, c_void_p]),
     "sfa_post_process": (ctypes.c_int, [c_void_p, i32, i32, i32, f32, f32, f32, f32, f32, f32, f32, f32, f32, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sfa_bvfeature_workspace_bytes": (sz, [i32, i64, ctypes.POINTER(SfaBvParams)]),
+    "sfa_bvfeature_rasterize": (ctypes.c_int, [c_void_p, c_void_p, i32, i64, ctypes.POINTER(SfaBvParams), c_void_p,
+                                               c_void_p, sz, c_void_p]),
     "sfa_project_boxes": (ctypes.c_int, [c_void_p, i32, c_void_p, i32, i32, c_void_p, i32, i32, i32, ctypes.c_double,
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sfa_pipeline_create": (c_void_p, [i32, i32, i64, ctypes.POINTER(SfaBevParams), c_void_p, i32, i32, i32, i32]),

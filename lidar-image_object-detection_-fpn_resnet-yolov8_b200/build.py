@@ -32,8 +32,21 @@ def find_nvcc():
     raise RuntimeError("nvcc not found")
 
 
+STAMP = LIB + ".flags"   # the variant (release / SFA_DEBUG_TIMING) the library on disk was built as
+
+
+def _variant():
+    return "debug-timing" if os.environ.get("SFA_DEBUG_TIMING") == "1" else "release"
+
+
 def _stale():
     if not os.path.exists(LIB):
+        return True
+    try:
+        with open(STAMP) as f:
+            if f.read().strip() != _variant():
+                return True
+    except OSError:
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, "sfa_b200.h"), __file__]
@@ -56,6 +69,8 @@ def build(force=False, verbose=False):
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libsfa_b200.so")
+    with open(STAMP, "w") as f:
+        f.write(_variant() + "\n")
     return LIB
 
 

@@ -220,6 +220,67 @@ def post_process_dense(detections, num_classes=3, down_ratio=4, peak_thresh=0.2,
     return res if real is None else res + (real,)
 
 
+def bv_params(discretization, boundary, point_floats=4):
+    """SfaBvParams the way makeBVFeature derives its geometry (argoverse_test.py:211-229, :248):
+    H, W in Python doubles; bounds, cell size and height range as the float32 values numpy uses when
+    the Python scalars meet the float32 sweep."""
+    f = np.float32
+    H = int((boundary["maxX"] - boundary["minX"]) / discretization)
+    W = int((boundary["maxY"] - boundary["minY"]) / discretization)
+    return _lib.SfaBvParams(f(boundary["minX"]), f(boundary["maxX"]), f(boundary["minY"]), f(boundary["maxY"]),
+                            f(boundary["minZ"]), f(boundary["maxZ"]), f(discretization),
+                            f(boundary["maxZ"] - boundary["minZ"]), H, W, int(point_floats))
+
+
+class BvFeatureRasterizer:
+    """makeBVFeature (argoverse_test.py:199-254) for batches of sweeps resident in HBM:
+    points float32 [sum N, point_floats] + int64 offsets [B+1] (or None for a uniform batch) ->
+    float32 [B, 3, H, W] = (density, height, intensity)."""
+
+    def __init__(self, discretization, boundary, point_floats=4, max_batch=64, max_points=262144, device=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("BvFeatureRasterizer needs a CUDA device (there is no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.params = bv_params(discretization, boundary, point_floats)
+        self.H, self.W, self.point_floats = self.params.height, self.params.width, int(point_floats)
+        if self.H <= 0 or self.W <= 0:
+            raise ValueError("empty map: %d x %d" % (self.H, self.W))
+        self.max_batch, self.max_points = int(max_batch), int(max_points)
+        self.ws_bytes = int(self.lib.sfa_bvfeature_workspace_bytes(self.max_batch, self.max_points,
+                                                                   ctypes.byref(self.params)))
+        if self.ws_bytes == 0:
+            raise _lib.SfaError(-1, _lib.last_error())
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+
+    def __call__(self, points, offsets=None, max_points=None, out=None):
+        _require_cuda(points, "points")
+        if points.dtype != torch.float32 or not points.is_contiguous():
+            raise TypeError("points must be a contiguous float32 tensor")
+        if offsets is None:
+            if points.dim() != 3 or points.shape[2] != self.point_floats:
+                raise ValueError("a uniform batch is [B, N, %d]" % self.point_floats)
+            B, max_points = points.shape[0], points.shape[1]
+        else:
+            _require_cuda(offsets, "offsets")
+            if offsets.dtype != torch.int64:
+                raise TypeError("offsets must be int64")
+            B = offsets.numel() - 1
+            if max_points is None:
+                raise ValueError("max_points (an upper bound of the longest sweep) is needed with offsets")
+        if B > self.max_batch:
+            raise ValueError("batch %d exceeds max_batch %d" % (B, self.max_batch))
+        if int(max_points) > self.max_points:
+            raise ValueError("max_points %d exceeds the %d the workspace was sized for" % (max_points, self.max_points))
+        if out is None:
+            out = torch.empty((B, 3, self.H, self.W), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sfa_bvfeature_rasterize(_ptr(points), _ptr(offsets), B, int(max_points),
+                                                        ctypes.byref(self.params), _ptr(out), _ptr(self.ws),
+                                                        self.ws_bytes, _stream_ptr(self.device)))
+        return out
+
+
 def pack_calibration(V2C, R0, P2, device=None):
     """Calibration matrices (data_process/kitti_data_utils.py:127-139: float32 V2C [3,4], R0 [3,3],
     P2 [3,4]; leading batch dimensions allowed, 4x4 homogeneous forms are cut down) -> float64

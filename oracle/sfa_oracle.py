@@ -308,6 +308,98 @@ def convert_det_to_real_values(detections, num_classes=3, geom: Geometry = KITTI
     return np.array(out)
 
 
+# ----------------------------------------------------------------------------- Argoverse raster
+ARGO_BV_BOUNDARY = {"minX": -40.0, "maxX": 40.0, "minY": -40.0, "maxY": 40.0, "minZ": -3.0, "maxZ": 1.0}
+ARGO_BV_DISCRETIZATION = 0.1   # argoverse_test.py:37-47
+# (discretization, boundary) sets the fixtures and parity tests run on: the scripts' own, a coarse
+# asymmetric one (400 x 300) and one whose cell count is not a multiple of 4 (150 x 109 -> scalar kernel paths)
+BV_TEST_GEOMS = {
+    "argo": (ARGO_BV_DISCRETIZATION, ARGO_BV_BOUNDARY),
+    "coarse": (0.2, {"minX": -20.0, "maxX": 60.0, "minY": -30.0, "maxY": 30.0, "minZ": -2.5, "maxZ": 3.5}),
+    "odd": (0.3, {"minX": -10.0, "maxX": 35.0, "minY": -12.5, "maxY": 20.2, "minZ": -1.7, "maxZ": 2.2})}
+
+
+def bv_feature_shape(discretization, boundary):
+    """argoverse_test.py:224-225."""
+    return (int((boundary["maxX"] - boundary["minX"]) / discretization),
+            int((boundary["maxY"] - boundary["minY"]) / discretization))
+
+
+def makeBVFeature(points, discretization, boundary):
+    """argoverse_test.py:199-254 restated without the per-point Python loop: max / max / count are
+    commutative, so ufunc.at gives the loop's result.  float32 sweeps [N, 3 or >= 4] ->
+    float32 [3, H, W] = (density, height, intensity)."""
+    if points.shape[1] == 3:
+        x, y, z = points[:, 0], points[:, 1], points[:, 2]
+        i = np.ones_like(x) * 0.5
+    elif points.shape[1] >= 4:
+        x, y, z, i = points[:, 0], points[:, 1], points[:, 2], points[:, 3]
+    else:
+        raise ValueError(f"Invalid point cloud shape: {points.shape}")
+    mask = ((x >= boundary["minX"]) & (x <= boundary["maxX"]) & (y >= boundary["minY"]) & (y <= boundary["maxY"]) &
+            (z >= boundary["minZ"]) & (z <= boundary["maxZ"]))
+    H, W = bv_feature_shape(discretization, boundary)
+    if not np.any(mask):
+        return np.zeros((3, H, W), dtype=np.float32)
+    x, y, z, i = x[mask], y[mask], z[mask], i[mask]
+    x_idx = np.clip(((boundary["maxX"] - x) / discretization).astype(np.int32), 0, H - 1)
+    y_idx = np.clip(((y - boundary["minY"]) / discretization).astype(np.int32), 0, W - 1)
+    h_map = np.zeros((H, W), dtype=np.float32)
+    d_map = np.zeros((H, W), dtype=np.float32)
+    i_map = np.zeros((H, W), dtype=np.float32)
+    z_rel = z - boundary["minZ"]
+    # the loop's `max(map[cell], v)` keeps the map value unless v > it: starting from +0.0, only
+    # values > 0 ever enter (no NaN, no -0.0)
+    zs, si = z_rel > 0, i > 0
+    np.maximum.at(h_map, (x_idx[zs], y_idx[zs]), z_rel[zs])
+    np.maximum.at(i_map, (x_idx[si], y_idx[si]), i[si])
+    np.add.at(d_map, (x_idx, y_idx), np.float32(1))
+    d_map = np.clip(d_map / 10.0, 0, 1)
+    with np.errstate(all="ignore"):
+        if h_map.max() > 0:
+            h_map = h_map / (boundary["maxZ"] - boundary["minZ"])
+        if i_map.max() > 0:
+            i_map = i_map / i_map.max()
+    return np.stack([d_map, h_map, i_map], axis=0).astype(np.float32)
+
+
+def synth_argoverse_sweep(seed, n=250_000, kind="uniform", boundary=ARGO_BV_BOUNDARY):
+    """float32 [n,4] sweeps for makeBVFeature: Argoverse-like (intensity 0..255), spilling 10 % over
+    each bound; `adversarial` adds grid-aligned coordinates, points on the bounds, negative / NaN /
+    zero intensities, NaN coordinates and a crowded cell."""
+    rng = np.random.default_rng(seed)
+    b = boundary
+    sx, sy, sz = b["maxX"] - b["minX"], b["maxY"] - b["minY"], b["maxZ"] - b["minZ"]
+    pts = np.empty((n, 4), dtype=np.float64)
+    pts[:, 0] = rng.uniform(b["minX"] - 0.1 * sx, b["maxX"] + 0.1 * sx, n)
+    pts[:, 1] = rng.uniform(b["minY"] - 0.1 * sy, b["maxY"] + 0.1 * sy, n)
+    pts[:, 2] = rng.uniform(b["minZ"] - 0.1 * sz, b["maxZ"] + 0.1 * sz, n)
+    pts[:, 3] = rng.integers(0, 256, n)
+    if kind == "adversarial" and n >= 64:
+        q = n // 8
+        pts[:q, 0] = np.round(pts[:q, 0] / 0.1) * 0.1                    # on cell edges
+        pts[:q, 1] = np.round(pts[:q, 1] / 0.1) * 0.1
+        pts[q:q + 6, 0] = [b["minX"], b["maxX"], b["minX"], b["maxX"], 0.0, -0.0]
+        pts[q:q + 6, 1] = [b["minY"], b["maxY"], b["maxY"], b["minY"], 0.0, -0.0]
+        pts[q:q + 6, 2] = [b["minZ"], b["maxZ"], b["minZ"], b["maxZ"], b["minZ"], b["maxZ"]]
+        pts[2 * q:2 * q + q // 2, 3] = -pts[2 * q:2 * q + q // 2, 3]     # negative intensity never wins over 0
+        pts[3 * q:3 * q + 50, 3] = np.nan
+        pts[3 * q + 50:3 * q + 100, 0] = np.nan
+        pts[3 * q + 100:3 * q + 150, 2] = np.inf
+        pts[4 * q:4 * q + q // 2, 3] = 0.0
+        pts[5 * q:5 * q + 40, :2] = [12.34, -7.89]                        # > 10 points in one cell: density saturates
+        pts[6 * q:7 * q, 2] = np.round(pts[6 * q:7 * q, 2] * 4) / 4       # z ties
+    elif kind == "xyz_only":
+        return pts[:, :3].astype(np.float32)
+    elif kind == "dark":
+        pts[:, 3] = 0.0                                                   # i_map.max() == 0: no normalisation
+    elif kind == "outside":
+        pts[:, 2] = b["maxZ"] + 5.0                                       # nothing passes the mask
+    elif kind == "wide":
+        return np.concatenate([pts, rng.uniform(0, 1, (n, 2))], axis=1).astype(np.float32)   # 6 columns
+    return pts.astype(np.float32)
+
+
 # ----------------------------------------------------------------------------- lidar boxes -> camera frame -> image (SURVEY.md §8f rank 2)
 def lidar_to_camera(x, y, z, V2C, R0):
     """data_process/transformation.py:50-60 with explicit calibration (V2C 3x4, R0 3x3)."""

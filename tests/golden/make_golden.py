@@ -12,6 +12,8 @@ seeded synthetic inputs, outputs stored here.  Nothing reads /root/reference at 
                      that the tests regenerate from the seed
   decode_small.npz   explicit heads + reference _nms/_topk/decode/post_processing/convert outputs
   decode_hashes.json sha256 pins at the full 152x152 head size, B=4, K=50
+  bvfeature_small.npz  small sweeps of every kind -> sparse reference makeBVFeature output
+                     (argoverse_test.py:199-254); bvfeature_hashes.json pins 250k-point sweeps
   projection_small.npz  post-processed detections + calibration -> the reference's lidar_to_camera_box
                      rows and convert_sfa3d_to_2d_boxes image boxes (test6.py:129-187), incl. boxes
                      behind the camera, straddling the image plane, outside the image and NaN rows
@@ -159,6 +161,38 @@ def make_decode(ns):
     return len(cases), len(hashes)
 
 
+BV_GEOMS = O.BV_TEST_GEOMS
+BV_KINDS = ["uniform", "adversarial", "xyz_only", "dark", "outside", "wide"]
+
+
+def make_bvfeature(ns):
+    small, c = {}, 0
+    for gname, (disc, bnd) in BV_GEOMS.items():
+        for kind in BV_KINDS:
+            pts = O.synth_argoverse_sweep(700 + c, 3000 if gname == "argo" else 2000, kind, bnd)
+            ref = ns.makeBVFeature(pts, disc, bnd)
+            assert ref.dtype == np.float32
+            tag = "c%02d" % c
+            small[tag + "_meta"] = np.array([gname, kind])
+            small[tag + "_pts"] = pts
+            flat = ref.ravel().view(np.uint32)
+            nz = np.flatnonzero(flat)
+            small[tag + "_nz"], small[tag + "_val"] = nz.astype(np.int64), flat[nz]
+            small[tag + "_shape"] = np.array(ref.shape)
+            c += 1
+    small["n_cases"] = np.array(c)
+    np.savez_compressed(os.path.join(HERE, "bvfeature_small.npz"), **small)
+    hashes = []
+    for seed, kind, n in ((800, "uniform", 250000), (801, "adversarial", 250000), (802, "xyz_only", 120000)):
+        pts = O.synth_argoverse_sweep(seed, n, kind)
+        ref = ns.makeBVFeature(pts, O.ARGO_BV_DISCRETIZATION, O.ARGO_BV_BOUNDARY)
+        hashes.append({"seed": seed, "kind": kind, "n": n, "input_sha256": sha(pts), "output_sha256": sha(ref),
+                       "occupied": int((ref[0] > 0).sum())})
+    with open(os.path.join(HERE, "bvfeature_hashes.json"), "w") as f:
+        json.dump(hashes, f, indent=1)
+    return c, len(hashes)
+
+
 class _Calib:
     def __init__(self, V2C, R0, P2):
         self.V2C, self.R0, self.P2 = V2C, R0, P2
@@ -221,6 +255,8 @@ def main():
         print("bev: %d small cases, %d hashed" % make_bev(ns))
     if not only or "decode" in only:
         print("decode: %d small cases, %d hashed" % make_decode(ns))
+    if not only or "bvfeature" in only:
+        print("bvfeature: %d small cases, %d hashed" % make_bvfeature(ns))
     if not only or "projection" in only:
         print("projection: %d cases" % make_projection(ns))
 

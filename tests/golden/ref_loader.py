@@ -113,6 +113,14 @@ def load():
         "test6.py", "convert_sfa3d_to_2d_boxes",
         {"np": __import__("numpy"), "convert_det_to_real_values": evl.convert_det_to_real_values,
          "lidar_to_camera_box": trf.lidar_to_camera_box})
+    ns.makeBVFeature_raw = _script_function("argoverse_test.py", "makeBVFeature", {"np": __import__("numpy")})
+
+    def makeBVFeature(*a, **k):
+        import numpy as np
+        with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+            return ns.makeBVFeature_raw(*a, **k)
+
+    ns.makeBVFeature = makeBVFeature
     _cache["ns"] = ns
     return ns
 

@@ -362,7 +362,7 @@ def test_bev_and_decode_in_a_cuda_graph(cuda_device):
         assert np.array_equal(det.cpu().numpy().view(np.uint32), want.view(np.uint32))
 
 
-@pytest.mark.parametrize("d", [50 / 608, 100 / 608, 0.1, 40 / 1000, 1.0, 3.0, 1e-3])
+@pytest.mark.parametrize("d", [50 / 608, 100 / 608, 0.1, 0.2, 0.3, 40 / 1000, 1.0, 3.0, 1e-3, 255.0, 4.0, 3.9, 6.0, 0.5, 97.0])
 def test_exact_division_matches_div_rn_over_every_float_in_range(cuda_device, d):
     """The hoisted-reciprocal division of bev_bin against the compiler's IEEE div.rn for EVERY float in
     [2^-30, 2^12) and its negative (2.8e8 bit patterns per sign, covers every coordinate a map can index), plus a

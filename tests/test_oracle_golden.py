@@ -172,3 +172,36 @@ def test_projection_oracle_against_reference_fixture():
         assert all(c >= 1 for c in conf)        # class 0 never passes: "confidence" is the class id
         total += len(boxes)
     assert total > 80
+
+
+# ----------------------------------------------------------------------------- makeBVFeature (Argoverse raster)
+def bv_dense(z, tag):
+    shape = tuple(int(v) for v in z[tag + "_shape"])
+    flat = np.zeros(int(np.prod(shape)), dtype=np.uint32)
+    flat[z[tag + "_nz"]] = z[tag + "_val"]
+    return flat.view(np.float32).reshape(shape)
+
+
+def test_bvfeature_oracle_against_reference_fixture():
+    BV_GEOMS = O.BV_TEST_GEOMS
+    z = np.load(os.path.join(GOLD, "bvfeature_small.npz"))
+    n = int(z["n_cases"])
+    assert n == 18
+    for c in range(n):
+        tag = "c%02d" % c
+        gname, kind = [str(v) for v in z[tag + "_meta"]]
+        disc, bnd = BV_GEOMS[gname]
+        want = bv_dense(z, tag)
+        got = O.makeBVFeature(z[tag + "_pts"], disc, bnd)
+        assert got.dtype == np.float32 and got.shape == want.shape == (3,) + O.bv_feature_shape(disc, bnd)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (gname, kind)
+
+
+def test_bvfeature_full_size_hashes():
+    with open(os.path.join(GOLD, "bvfeature_hashes.json")) as f:
+        rows = json.load(f)
+    for row in rows:
+        pts = O.synth_argoverse_sweep(row["seed"], row["n"], row["kind"])
+        assert sha(pts) == row["input_sha256"]
+        out = O.makeBVFeature(pts, O.ARGO_BV_DISCRETIZATION, O.ARGO_BV_BOUNDARY)
+        assert sha(out) == row["output_sha256"] and int((out[0] > 0).sum()) == row["occupied"]

@@ -85,3 +85,16 @@ def test_projection_oracle_equals_reference(ns, seed):
         want = ns.convert_sfa3d_to_2d_boxes(sample, _Calib(V2C, R0, P2), (375, 1242))
         assert want == O.convert_sfa3d_to_2d_boxes(sample, V2C, R0, P2, (375, 1242))
         assert len(want[0]) > 5
+
+
+@pytest.mark.parametrize("gname,kind,n,seed", [
+    ("argo", "uniform", 100000, 31), ("argo", "adversarial", 100000, 32), ("coarse", "adversarial", 50000, 33),
+    ("odd", "wide", 20000, 34), ("argo", "xyz_only", 20000, 35), ("argo", "outside", 1000, 36), ("odd", "dark", 5000, 37)])
+def test_bvfeature_oracle_equals_reference(ns, gname, kind, n, seed):
+    """makeBVFeature (argoverse_test.py:199-254, compiled out of the script) vs the loop-free restatement."""
+    disc, bnd = O.BV_TEST_GEOMS[gname]
+    pts = O.synth_argoverse_sweep(seed, n, kind, bnd)
+    want = ns.makeBVFeature(pts, disc, bnd)
+    got = O.makeBVFeature(pts, disc, bnd)
+    assert want.dtype == got.dtype == np.float32 and want.shape == got.shape
+    assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
