@@ -65,6 +65,8 @@ PROTOTYPES = {
                                   c_void_p, i32, c_void_p, sz, c_void_p]),
     "sfa_post_process": (ctypes.c_int, [c_void_p, i32, i32, i32, f32, f32, f32, f32, f32, f32, f32, f32, f32, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sfa_transform_points": (ctypes.c_int, [c_void_p, i32, i32, c_void_p, i32, i64, c_void_p, i32, c_void_p, c_void_p, i32,
+                                            i32, c_void_p]),
     "sfa_bvfeature_workspace_bytes": (sz, [i32, i64, ctypes.POINTER(SfaBvParams)]),
     "sfa_bvfeature_rasterize": (ctypes.c_int, [c_void_p, c_void_p, i32, i64, ctypes.POINTER(SfaBvParams), c_void_p,
                                                c_void_p, sz, c_void_p]),

@@ -220,6 +220,64 @@ def post_process_dense(detections, num_classes=3, down_ratio=4, peak_thresh=0.2,
     return res if real is None else res + (real,)
 
 
+def transform_points_device(points, mats=None, scales=None, offsets=None, max_points=None, out=None,
+                            out_dtype=torch.float32):
+    """point_transform / Random_Rotation / Random_Scaling on sweeps resident in HBM
+    (data_process/transformation.py:242-285, :349-352, :366-368).
+      points  CUDA float32/float64 [B, N, S] (uniform batch) or [sum N, S] with int64 offsets [B+1]; S >= 3
+      mats    CUDA float64 [B, m, 4, 4] (or [m, 4, 4] for one sweep): applied in order as [x y z 1] @ M
+      scales  CUDA float32 [B]: float32 x, y, z times the factor, after the matrices
+      out     result tensor (same layout; pass `points` itself for the in-place form) or None
+    Returns float32 [.., S] (the sweep as the reference leaves it) or, with out_dtype=torch.float64 and
+    no out, float64 [.., 3] (what point_transform returns)."""
+    lib = _lib.load()
+    _require_cuda(points, "points")
+    if points.dtype not in (torch.float32, torch.float64) or not points.is_contiguous():
+        raise TypeError("points must be a contiguous float32 / float64 tensor")
+    if offsets is None:
+        if points.dim() == 2:
+            points_b = points[None]
+        elif points.dim() == 3:
+            points_b = points
+        else:
+            raise ValueError("points must be [N, S] or [B, N, S]")
+        B, max_points = points_b.shape[0], points_b.shape[1]
+    else:
+        _require_cuda(offsets, "offsets")
+        if offsets.dtype != torch.int64 or points.dim() != 2:
+            raise TypeError("ragged batches are [sum N, S] points with int64 offsets")
+        B = offsets.numel() - 1
+        if max_points is None:
+            raise ValueError("max_points (an upper bound of the longest sweep) is needed with offsets")
+    S = points.shape[-1]
+    n_mats = 0
+    if mats is not None:
+        _require_cuda(mats, "mats")
+        if mats.dim() == 3:
+            mats = mats[None]
+        if mats.dtype != torch.float64 or mats.dim() != 4 or mats.shape[0] != B or tuple(mats.shape[2:]) != (4, 4):
+            raise ValueError("mats must be float64 [B, m, 4, 4]")
+        mats = mats.contiguous()
+        n_mats = mats.shape[1]
+    if scales is not None:
+        _require_cuda(scales, "scales")
+        if scales.dtype != torch.float32 or scales.numel() != B:
+            raise ValueError("scales must be float32 [B]")
+        scales = scales.contiguous()
+    if out is None:
+        if out_dtype == torch.float64:
+            out = torch.empty(points.shape[:-1] + (3,), dtype=torch.float64, device=points.device)
+        else:
+            out = torch.empty(points.shape, dtype=torch.float32, device=points.device)
+    elif out.shape[:-1] != points.shape[:-1] or not out.is_contiguous() or out.dtype not in (torch.float32, torch.float64):
+        raise ValueError("out must be a contiguous float tensor with the points' leading shape")
+    with torch.cuda.device(points.device):
+        _lib.check(lib.sfa_transform_points(_ptr(points), int(points.dtype == torch.float64), S, _ptr(offsets), B,
+                                            int(max_points), _ptr(mats), n_mats, _ptr(scales), _ptr(out),
+                                            int(out.dtype == torch.float64), out.shape[-1], _stream_ptr(points.device)))
+    return out
+
+
 def bv_params(discretization, boundary, point_floats=4):
     """SfaBvParams the way makeBVFeature derives its geometry (argoverse_test.py:211-229, :248):
     H, W in Python doubles; bounds, cell size and height range as the float32 values numpy uses when

@@ -308,6 +308,61 @@ def convert_det_to_real_values(detections, num_classes=3, geom: Geometry = KITTI
     return np.array(out)
 
 
+# ----------------------------------------------------------------------------- training-side point augmentation
+def point_transform(points, tx, ty, tz, rx=0, ry=0, rz=0):
+    """data_process/transformation.py:242-285: homogeneous row vectors times a translation matrix and
+    up to three rotation matrices, each a separate float64 matmul.  (numpy's dgemm accumulates the four
+    products of a row in order with fused multiply-adds; the CUDA kernel does the same.)"""
+    N = points.shape[0]
+    points = np.hstack([points, np.ones((N, 1))])
+    mat1 = np.eye(4)
+    mat1[3, 0:3] = tx, ty, tz
+    points = np.matmul(points, mat1)
+    for angle, (a, b) in ((rx, (1, 2)), (ry, (2, 0)), (rz, (0, 1))):
+        if angle != 0:
+            points = np.matmul(points, rotation_matrix(angle, a, b))
+    return points[:, 0:3]
+
+
+def rotation_matrix(angle, a, b):
+    """The 4x4 matrices of transformation.py:256-283: rotation in the (a, b) plane,
+    mat[a,a] = mat[b,b] = cos, mat[a,b] = -sin, mat[b,a] = sin."""
+    mat = np.zeros((4, 4))
+    for k in range(4):
+        if k not in (a, b):
+            mat[k, k] = 1
+    mat[a, a] = np.cos(angle)
+    mat[a, b] = -np.sin(angle)
+    mat[b, a] = np.sin(angle)
+    mat[b, b] = np.cos(angle)
+    return mat
+
+
+def transform_matrices(tx, ty, tz, rx=0, ry=0, rz=0):
+    """The matmul chain of point_transform as a list of 4x4 float64 matrices."""
+    mat1 = np.eye(4)
+    mat1[3, 0:3] = tx, ty, tz
+    mats = [mat1]
+    for angle, (a, b) in ((rx, (1, 2)), (ry, (2, 0)), (rz, (0, 1))):
+        if angle != 0:
+            mats.append(rotation_matrix(angle, a, b))
+    return mats
+
+
+def random_rotation_points(lidar, angle):
+    """Random_Rotation.__call__ on the sweep (transformation.py:349-352): float32 in place."""
+    lidar = lidar.copy()
+    lidar[:, 0:3] = point_transform(lidar[:, 0:3], 0, 0, 0, rz=angle)
+    return lidar
+
+
+def random_scaling_points(lidar, factor):
+    """Random_Scaling.__call__ on the sweep (transformation.py:366-368): float32 times a Python float."""
+    lidar = lidar.copy()
+    lidar[:, 0:3] = lidar[:, 0:3] * factor
+    return lidar
+
+
 # ----------------------------------------------------------------------------- Argoverse raster (SURVEY.md §8f rank 4)
 ARGO_BV_BOUNDARY = {"minX": -40.0, "maxX": 40.0, "minY": -40.0, "maxY": 40.0, "minZ": -3.0, "maxZ": 1.0}
 ARGO_BV_DISCRETIZATION = 0.1   # argoverse_test.py:37-47

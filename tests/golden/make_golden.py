@@ -14,6 +14,8 @@ seeded synthetic inputs, outputs stored here.  Nothing reads /root/reference at 
   decode_hashes.json sha256 pins at the full 152x152 head size, B=4, K=50
   bvfeature_small.npz  small sweeps of every kind -> sparse reference makeBVFeature output
                      (argoverse_test.py:199-254); bvfeature_hashes.json pins 250k-point sweeps
+  augment_small.npz  sweep -> the reference's point_transform (float64), Random_Rotation and
+                     Random_Scaling results (float32 sweeps, seeded np.random; data_process/transformation.py)
   projection_small.npz  post-processed detections + calibration -> the reference's lidar_to_camera_box
                      rows and convert_sfa3d_to_2d_boxes image boxes (test6.py:129-187), incl. boxes
                      behind the camera, straddling the image plane, outside the image and NaN rows
@@ -193,6 +195,31 @@ def make_bvfeature(ns):
     return c, len(hashes)
 
 
+AUG_PARAMS = [(0, 0, 0, 0, 0, 0.3), (1.5, -2.0, 0.25, 0, 0, -0.7), (0, 0, 0, 0.1, 0.2, 0.3), (0.1, 0.2, 0.3, 0, 0, 0),
+              (0, 0, 0, 0, 0, np.pi / 4), (0, 0, 0, -1.3, 0, 0)]
+
+
+def make_augment(ns):
+    small = {}
+    sweep = O.synth_sweep(600, 4000, O.KITTI, "outside")
+    small["sweep"] = sweep
+    small["params"] = np.array(AUG_PARAMS, dtype=np.float64)
+    for k, prm in enumerate(AUG_PARAMS):
+        small["pt%d" % k] = ns.point_transform(sweep[:, 0:3], *prm)
+        small["pt%d_f64in" % k] = ns.point_transform(sweep[:, 0:3].astype(np.float64) * 1.000001, *prm)
+    labels = np.array([[10.0, 1.0, -1.0, 1.5, 1.6, 4.0, 0.3], [30.0, -5.0, -0.8, 1.6, 1.7, 4.2, -1.0]])
+    for k, seed in enumerate((1, 2, 3, 4)):
+        np.random.seed(seed)
+        lidar, _ = ns.Random_Rotation(limit_angle=np.pi / 4, p=1.0)(sweep.copy(), labels.copy())
+        small["rot%d" % k], small["rot%d_next" % k] = lidar, np.array(np.random.random())
+        np.random.seed(seed)
+        lidar, lab = ns.Random_Scaling(scaling_range=(0.95 + 0.01 * k, 1.05), p=1.0)(sweep.copy(), labels.copy())
+        small["scl%d" % k], small["scl%d_labels" % k], small["scl%d_next" % k] = lidar, lab, np.array(np.random.random())
+    small["labels"] = labels
+    np.savez_compressed(os.path.join(HERE, "augment_small.npz"), **small)
+    return len(AUG_PARAMS), 4
+
+
 class _Calib:
     def __init__(self, V2C, R0, P2):
         self.V2C, self.R0, self.P2 = V2C, R0, P2
@@ -257,6 +284,8 @@ def main():
         print("decode: %d small cases, %d hashed" % make_decode(ns))
     if not only or "bvfeature" in only:
         print("bvfeature: %d small cases, %d hashed" % make_bvfeature(ns))
+    if not only or "augment" in only:
+        print("augment: %d point_transform cases, %d seeded draws" % make_augment(ns))
     if not only or "projection" in only:
         print("projection: %d cases" % make_projection(ns))
 

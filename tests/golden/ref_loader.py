@@ -109,6 +109,8 @@ def load():
     ns.post_processing_pristine = post_processing_pristine
     ns.convert_det_to_real_values = evl.convert_det_to_real_values
     ns.lidar_to_camera_box = trf.lidar_to_camera_box
+    ns.point_transform = trf.point_transform
+    ns.Random_Rotation, ns.Random_Scaling = trf.Random_Rotation, trf.Random_Scaling
     ns.convert_sfa3d_to_2d_boxes = _script_function(
         "test6.py", "convert_sfa3d_to_2d_boxes",
         {"np": __import__("numpy"), "convert_det_to_real_values": evl.convert_det_to_real_values,

@@ -205,3 +205,23 @@ def test_bvfeature_full_size_hashes():
         assert sha(pts) == row["input_sha256"]
         out = O.makeBVFeature(pts, O.ARGO_BV_DISCRETIZATION, O.ARGO_BV_BOUNDARY)
         assert sha(out) == row["output_sha256"] and int((out[0] > 0).sum()) == row["occupied"]
+
+
+# ----------------------------------------------------------------------------- training-side sweep augmentation
+def test_augmentation_oracle_against_reference_fixture():
+    z = np.load(os.path.join(GOLD, "augment_small.npz"))
+    sweep = z["sweep"]
+    for k, prm in enumerate(z["params"]):
+        got = O.point_transform(sweep[:, 0:3], *prm)
+        assert got.dtype == np.float64 and np.array_equal(got, z["pt%d" % k])
+        chain = np.hstack([sweep[:, 0:3], np.ones((len(sweep), 1))])
+        for m in O.transform_matrices(*prm):
+            chain = np.matmul(chain, m)
+        assert np.array_equal(chain[:, 0:3], z["pt%d" % k])
+    for k, seed in enumerate((1, 2, 3, 4)):
+        np.random.seed(seed)
+        assert np.random.random() <= 1.0
+        angle = np.random.uniform(-np.pi / 4, np.pi / 4)
+        assert np.array_equal(O.random_rotation_points(sweep, angle).view(np.uint32), z["rot%d" % k].view(np.uint32))
+        lo = 0.95 + 0.01 * k
+        assert np.array_equal(O.random_scaling_points(sweep, lo).view(np.uint32), z["scl%d" % k].view(np.uint32))
