@@ -97,6 +97,27 @@ class BevRasterizer:
         return n
 
 
+class FrontBackRasterizer:
+    """The front + back pair of the 2-sides demo (data_process/demo_dataset.py:70-88): the same sweeps
+    filtered and rasterised once with cnf.boundary and once with cnf.boundary_back (negative x rows wrap
+    like numpy's negative indices).  Two passes of the kernels over the device-resident sweeps on one
+    stream, sharing one workspace; returns (front [B,3,H,W], back [B,3,H,W])."""
+
+    def __init__(self, cnf=None, max_batch: int = 64, max_points: int = 131072, device=None):
+        from .config import kitti_config
+        from . import geometry
+        cnf = kitti_config if cnf is None else cnf
+        self.front = BevRasterizer(geometry.from_config(cnf, cnf.boundary), max_batch, max_points, device)
+        self.back = BevRasterizer.__new__(BevRasterizer)
+        self.back.__dict__.update(self.front.__dict__)                      # same workspace, table and status word
+        self.back.geom = geometry.from_config(cnf, cnf.boundary_back)
+
+    def __call__(self, points, offsets, max_points, out=None):
+        front_out, back_out = (None, None) if out is None else out
+        return (self.front(points, offsets, max_points, out=front_out),
+                self.back(points, offsets, max_points, out=back_out))
+
+
 def filter_lidar_device(points, geom: BevGeometry):
     """get_filtered_lidar (data_process/kitti_data_utils.py:228-241) on a CUDA [N,4] sweep:
     returns the filtered, z-shifted sweep as a new CUDA tensor (one host sync to size it)."""

@@ -407,3 +407,30 @@ def test_bev_random_geometries(cuda_device):
         got, rast = _run_batch(cuda_device, [sweep], g)
         _assert_bit_exact(got[0], want, "trial %d H=%d W=%d d=%g minX=%g" % (trial, H, W, d, min_x))
         assert rast.out_of_map_points() == 0
+
+
+def test_front_and_back_pair_of_the_two_sides_demo(cuda_device):
+    """demo_dataset.py:70-88: one sweep around the sensor, rasterised with cnf.boundary and with
+    cnf.boundary_back (rows of negative x wrap; points with x == 0 land in both maps)."""
+    fast = pkg("fast")
+    rng = np.random.default_rng(77)
+    sweeps = []
+    for n in (60000, 1, 33333):
+        pts = np.empty((n, 4), dtype=np.float32)
+        pts[:, 0] = rng.uniform(-55, 55, n)
+        pts[:, 1] = rng.uniform(-27, 27, n)
+        pts[:, 2] = np.round(rng.uniform(-3, 1.5, n) * 8) / 8
+        pts[:, 3] = rng.uniform(0, 1, n)
+        pts[: n // 50, 0] = 0.0
+        pts[n // 50: n // 25, 0] = -0.0
+        sweeps.append(pts)
+    lens = [s.shape[0] for s in sweeps]
+    offsets = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int64, device=cuda_device)
+    pts = torch.from_numpy(np.concatenate(sweeps)).to(cuda_device)
+    pair = fast.FrontBackRasterizer(max_batch=3, max_points=max(lens), device=cuda_device)
+    front, back = pair(pts, offsets, max(lens))
+    for i, s in enumerate(sweeps):
+        _assert_bit_exact(front[i].cpu().numpy(), O.make_bev_scatter(s, O.KITTI, True, np.float32), "front %d" % i)
+        _assert_bit_exact(back[i].cpu().numpy(), O.make_bev_scatter(s, O.KITTI_BACK, True, np.float32), "back %d" % i)
+    assert float(back[0, 2, 0].sum()) > 0 and float(front[0, 2, 0].sum()) > 0      # the x == 0 points, row 0 of both
+    assert pair.front.out_of_map_points() == 0
