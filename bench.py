@@ -530,7 +530,7 @@ def run_b200(args):
             "e2e": e2e, "roofline": roofline, "roofline_path": roofline_path, "kernels": kern,
             "cpu_baseline": cpu_baseline, "clocks": clocks.summary(t_begin, t_end),
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -563,7 +563,20 @@ def run_reference(args):
                          "cpu": cpu_model_name()},
         "e2e": {"value": round(v, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_RESULT_FD = None
+
+
+def emit(line):
+    """The ONE line of this run on the real stdout (see main)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
@@ -584,6 +597,12 @@ def main():
                     help="profiling aid (ncu): plain launches instead of CUDA-graph replays, exactly W warm-up steps; "
                          "the printed value is not a bench number")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: whatever libraries print meanwhile (NCCL's version banner under
+    # torchrun, warnings of worker processes) is routed to stderr
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         args.steps = 4 if args.steps is None else args.steps
         args.warmup = 1 if args.warmup is None else args.warmup
