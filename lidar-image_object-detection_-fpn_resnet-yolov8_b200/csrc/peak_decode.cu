@@ -9,9 +9,10 @@
 //
 // Two kernels per batch, nothing but the candidate list in between (it lives in L2):
 //
-//   peak_candidates : one CTA per (frame, slab of 8 rows, all classes).  Stages slab + halo rows in
+//   peak_candidates : one CTA per (frame, slab of 16 rows, all classes).  Stages slab + halo rows in
 //     shared memory as ORDERABLE 32-bit keys (16-B coalesced loads), applies the 3x3 peak-keep in the
-//     key domain with one thread walking one (class, x) column (3 shared loads per cell), and
+//     key domain — a thread takes 4 columns x 4 rows (16-B shared loads, 3-input max), or, in tiles
+//     that hold NaN / inf, walks one (class, x) column with the full heat * keep semantics — and
 //     appends every cell whose kept value is > 0 to the frame's candidate list as a 64-bit word
 //     (key << 32 | ~linear_index): one block-wide scan and ONE global atomicAdd per CTA.  In any
 //     frame with at least K positive peaks these are the only cells that can reach the top K.
@@ -85,11 +86,11 @@ __device__ __forceinline__ uint32_t kept_key(uint32_t own, uint32_t m, bool do_n
     return (own == kPosInfKey || own == kNegInfKey) ? kNanKey : kZeroKey;
 }
 
-__global__ void __launch_bounds__(kCandThreads)
+__global__ void __launch_bounds__(kCandThreads, 4)
 peak_candidates_kernel(DecodeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned int warp_sums[kCandWarps];
-    __shared__ unsigned int list_base, grp_min, grp_nmin;
+    __shared__ unsigned int list_base, grp_min, grp_max, grp_nmin;
     __shared__ uint32_t capbits[kCapClasses * kCandRows * kCapWords];   // bitmap of the group's lowest-key cells
     __shared__ uint32_t caprow[kCapClasses * kCandRows];                // per (class, row): cells before it
     uint32_t* tkeys = reinterpret_cast<uint32_t*>(smem_raw);   // [C][kCandRows + 2][w]
@@ -101,7 +102,7 @@ peak_candidates_kernel(DecodeArgs a) {
     constexpr int trows = kCandRows + 2;
     const int tplane = trows * w;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { grp_min = 0xFFFFFFFFu; grp_nmin = 0; }
+    if (tid == 0) { grp_min = 0xFFFFFFFFu; grp_max = 0; grp_nmin = 0; }
     __syncthreads();   // before any warp's atomicMin on grp_min
 
     // ---- stage slab + halo rows (r0-1 .. r0+rows) as orderable keys ---------------------------------
@@ -110,6 +111,7 @@ peak_candidates_kernel(DecodeArgs a) {
     // -inf, whose key is 0x007FFFFF).  NaN maps to the largest key, so an integer max propagates it
     // exactly like ATen's max_pool2d does.
     uint32_t tile_min = 0xFFFFFFFFu;   // lowest key among the tile's in-map cells (see "plateau cap" below)
+    uint32_t tile_max = 0;             // highest one: >= the +inf key means an inf or NaN somewhere in the tile
     {
         const float* hmb = a.hm + (size_t)b * C * hw;
         const int y_lo = r0 - 1;
@@ -131,6 +133,7 @@ peak_candidates_kernel(DecodeArgs a) {
                     k = make_uint4(orderable_u32(act(v.x, sg), kNanKey), orderable_u32(act(v.y, sg), kNanKey),
                                    orderable_u32(act(v.z, sg), kNanKey), orderable_u32(act(v.w, sg), kNanKey));
                     tile_min = min(tile_min, min(min(k.x, k.y), min(k.z, k.w)));
+                    tile_max = max(tile_max, max(max(k.x, k.y), max(k.z, k.w)));
                 }
                 dst[i] = k;
                 t4 += kCandThreads;
@@ -151,42 +154,94 @@ peak_candidates_kernel(DecodeArgs a) {
         }
     }
     tile_min = __reduce_min_sync(0xFFFFFFFFu, tile_min);
-    if (lane == 0) atomicMin(&grp_min, tile_min);
+    tile_max = __reduce_max_sync(0xFFFFFFFFu, tile_max);
+    if (lane == 0) { atomicMin(&grp_min, tile_min); atomicMax(&grp_max, tile_max); }
     __syncthreads();
     const uint32_t vmin = grp_min;
+
+    // ---- fast walker: 4 columns x 4 rows per thread on a separable 3x3 max ------------------------------
+    // Block-uniform choice.  Without +-inf / NaN in the tile (vmin above the -inf key, the maximum below the
+    // +inf key) the kept value of a cell is simply "own if own == max3x3 else 0", so a cell is listed iff
+    // own == max3x3 and own > 0.  A thread takes a quad of columns and 4 slab rows: per tile row one 16-B
+    // shared load plus the two neighbours left and right of the quad, and one 3-input max per cell each for
+    // the horizontal and the vertical direction.
+    const bool quad = a.vec4 && a.do_nms && vmin > kNegInfKey && grp_max < kPosInfKey;
 
     // ---- one thread walks one (class, x) column down the slab ---------------------------------------
     const size_t frame_cap = (size_t)C * hw;
     unsigned long long* list = a.cands + (size_t)b * frame_cap;
     const int ncols = C * w;
+    // A thread's cells are the set bits of posmask / minmask.  Scalar walker: bit r = slab row r of column
+    // (c, x).  Quad walker: bit 4*i + j = slab row rg*4 + i of column (c, x + j).
     for (int col0 = 0; col0 < ncols; col0 += kCandThreads) {   // block-uniform trip count (barriers inside)
-        const int col = col0 + tid;
-        const bool valid = col < ncols;
-        const int c = valid ? col / w : 0;
-        const int x = valid ? col - c * w : 0;
+        int c = 0, x = 0, rg = 0;
         unsigned posmask = 0, minmask = 0;
-        if (valid) {
-            const uint32_t* t = tkeys + (size_t)c * tplane + x;   // tile row 0 (halo above the slab)
-            const bool has_l = x > 0, has_r = x < w - 1;
-            uint32_t own = t[w];
-            uint32_t h_prev = t[0], h_cur = own;
-            if (has_l) { h_prev = max(h_prev, t[-1]); h_cur = max(h_cur, t[w - 1]); }
-            if (has_r) { h_prev = max(h_prev, t[1]); h_cur = max(h_cur, t[w + 1]); }
+        if (quad) {
+            const int q = (col0 >> 2) + (tid & (kCandThreads / 4 - 1));   // quad of columns; kCandThreads / 4 quads per pass
+            rg = tid / (kCandThreads / 4);                                  // 4 slab rows each
+            const int w4 = w >> 2;
+            if (q < (ncols >> 2) && rg * 4 < rows) {
+                c = q / w4;
+                x = (q - c * w4) * 4;
+                const uint32_t* tk = tkeys + (size_t)c * tplane + x;
+                const bool has_l = x > 0, has_r = x + 4 < w;
+                uint4 own;
+                auto hrow = [&](int tr) -> uint4 {   // horizontal 3-max of the quad in tile row tr; own = the row's keys
+                    own = *reinterpret_cast<const uint4*>(tk + tr * w);
+                    const uint32_t l = has_l ? tk[tr * w - 1] : 0u;
+                    const uint32_t r = has_r ? tk[tr * w + 4] : 0u;
+                    return make_uint4(max(max(l, own.x), own.y), max(max(own.x, own.y), own.z),
+                                      max(max(own.y, own.z), own.w), max(max(own.z, own.w), r));
+                };
+                uint4 h0 = hrow(rg * 4), h1 = hrow(rg * 4 + 1);
+                uint4 cur = own;   // keys of tile row rg*4 + 1 = slab row rg*4
 #pragma unroll
-            for (int r = 0; r < kCandRows; ++r) {
-                if (r < rows) {
-                    const uint32_t* nx = t + (r + 2) * w;
-                    const uint32_t own_next = nx[0];
-                    uint32_t h_next = own_next;
-                    if (has_l) h_next = max(h_next, nx[-1]);
-                    if (has_r) h_next = max(h_next, nx[1]);
-                    const uint32_t kept = kept_key(own, max(max(h_prev, h_cur), h_next), a.do_nms != 0);
-                    if (kept > kZeroKey) posmask |= 1u << r;
-                    if (kept > kZeroKey && kept == vmin) minmask |= 1u << r;
-                    h_prev = h_cur; h_cur = h_next; own = own_next;
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 h2 = hrow(rg * 4 + i + 2);
+                    const uint4 nxt = own;
+                    if (rg * 4 + i < rows) {
+                        const uint32_t m0 = max(max(h0.x, h1.x), h2.x), m1 = max(max(h0.y, h1.y), h2.y);
+                        const uint32_t m2 = max(max(h0.z, h1.z), h2.z), m3 = max(max(h0.w, h1.w), h2.w);
+                        const unsigned p = (m0 == cur.x && cur.x > kZeroKey ? 1u : 0u) | (m1 == cur.y && cur.y > kZeroKey ? 2u : 0u) |
+                                           (m2 == cur.z && cur.z > kZeroKey ? 4u : 0u) | (m3 == cur.w && cur.w > kZeroKey ? 8u : 0u);
+                        const unsigned e = (cur.x == vmin ? 1u : 0u) | (cur.y == vmin ? 2u : 0u) | (cur.z == vmin ? 4u : 0u) |
+                                           (cur.w == vmin ? 8u : 0u);
+                        posmask |= p << (4 * i);
+                        minmask |= (p & e) << (4 * i);
+                    }
+                    h0 = h1; h1 = h2; cur = nxt;
+                }
+            }
+        } else {
+            const int col = col0 + tid;
+            const bool valid = col < ncols;
+            c = valid ? col / w : 0;
+            x = valid ? col - c * w : 0;
+            if (valid) {
+                const uint32_t* t = tkeys + (size_t)c * tplane + x;   // tile row 0 (halo above the slab)
+                const bool has_l = x > 0, has_r = x < w - 1;
+                uint32_t own = t[w];
+                uint32_t h_prev = t[0], h_cur = own;
+                if (has_l) { h_prev = max(h_prev, t[-1]); h_cur = max(h_cur, t[w - 1]); }
+                if (has_r) { h_prev = max(h_prev, t[1]); h_cur = max(h_cur, t[w + 1]); }
+#pragma unroll
+                for (int r = 0; r < kCandRows; ++r) {
+                    if (r < rows) {
+                        const uint32_t* nx = t + (r + 2) * w;
+                        const uint32_t own_next = nx[0];
+                        uint32_t h_next = own_next;
+                        if (has_l) h_next = max(h_next, nx[-1]);
+                        if (has_r) h_next = max(h_next, nx[1]);
+                        const uint32_t kept = kept_key(own, max(max(h_prev, h_cur), h_next), a.do_nms != 0);
+                        if (kept > kZeroKey) posmask |= 1u << r;
+                        if (kept > kZeroKey && kept == vmin) minmask |= 1u << r;
+                        h_prev = h_cur; h_cur = h_next; own = own_next;
+                    }
                 }
             }
         }
+        auto cell_x = [&](int bit) -> int { return quad ? x + (bit & 3) : x; };
+        auto cell_r = [&](int bit) -> int { return quad ? rg * 4 + (bit >> 2) : bit; };
         // ---- plateau cap ---------------------------------------------------------------------------
         // Among cells with EQUAL keys the top-K takes the lowest linear indices, so of the cells of this
         // column group that share one key only the K lowest-index ones can ever be selected.  Applied to
@@ -194,9 +249,9 @@ peak_candidates_kernel(DecodeArgs a) {
         // plateaus at, or a constant map — this keeps such maps from listing every cell (69 k words per
         // frame) without changing any result; where the lowest cell is no kept peak (any ordinary map)
         // it costs one warp reduction and one barrier.
-        const uint32_t* tcol = tkeys + (size_t)c * tplane + x;
-        auto key_at = [&](int r) -> uint32_t {   // a positive kept cell keeps its own key, except -inf under a
-            const uint32_t own = tcol[(r + 1) * w];   // larger neighbour (-inf * 0 = NaN)
+        const uint32_t* tcls = tkeys + (size_t)c * tplane;
+        auto key_at = [&](int cx, int r) -> uint32_t {   // a positive kept cell keeps its own key, except -inf under a
+            const uint32_t own = tcls[(r + 1) * w + cx];   // larger neighbour (-inf * 0 = NaN)
             return (a.do_nms && own == kNegInfKey) ? kNanKey : own;
         };
         {
@@ -212,8 +267,10 @@ peak_candidates_kernel(DecodeArgs a) {
             for (int i = tid; i < n_rows * kCapWords; i += kCandThreads) capbits[i] = 0;
             __syncthreads();
             const int row0 = (c - c_first) * kCandRows;
-            for (unsigned m = minmask; m; m &= m - 1)
-                atomicOr(&capbits[(row0 + __ffs(m) - 1) * kCapWords + (x >> 5)], 1u << (x & 31));
+            for (unsigned m = minmask; m; m &= m - 1) {
+                const int bit = __ffs(m) - 1, cx = cell_x(bit);
+                atomicOr(&capbits[(row0 + cell_r(bit)) * kCapWords + (cx >> 5)], 1u << (cx & 31));
+            }
             __syncthreads();
             if (tid < n_rows) {
                 unsigned tot = 0;
@@ -238,11 +295,11 @@ peak_candidates_kernel(DecodeArgs a) {
             }
             __syncthreads();
             for (unsigned m = minmask; m; m &= m - 1) {
-                const int r = __ffs(m) - 1;
+                const int bit = __ffs(m) - 1, cx = cell_x(bit), r = cell_r(bit);
                 const uint32_t* rowbits = capbits + (row0 + r) * kCapWords;
-                unsigned rank = caprow[row0 + r] + __popc(rowbits[x >> 5] & ((1u << (x & 31)) - 1u));
-                for (int j = 0; j < (x >> 5); ++j) rank += __popc(rowbits[j]);
-                if (rank >= (unsigned)a.K) posmask &= ~(1u << r);   // K lower-index cells of the same key exist
+                unsigned rank = caprow[row0 + r] + __popc(rowbits[cx >> 5] & ((1u << (cx & 31)) - 1u));
+                for (int j = 0; j < (cx >> 5); ++j) rank += __popc(rowbits[j]);
+                if (rank >= (unsigned)a.K) posmask &= ~(1u << bit);   // K lower-index cells of the same key exist
             }
         }
 
@@ -269,10 +326,11 @@ peak_candidates_kernel(DecodeArgs a) {
         __syncthreads();
         size_t at = (size_t)list_base + warp_sums[warp] + incl - cnt;
         while (posmask) {
-            const int r = __ffs(posmask) - 1;
+            const int bit = __ffs(posmask) - 1;
             posmask &= posmask - 1;
-            const uint32_t lin = (uint32_t)(c * hw + (r0 + r) * w + x);
-            list[at++] = ((unsigned long long)key_at(r) << 32) | (unsigned long long)(0xFFFFFFFFu - lin);
+            const int cx = cell_x(bit), r = cell_r(bit);
+            const uint32_t lin = (uint32_t)(c * hw + (r0 + r) * w + cx);
+            list[at++] = ((unsigned long long)key_at(cx, r) << 32) | (unsigned long long)(0xFFFFFFFFu - lin);
         }
         if (tid == 0) grp_nmin = 0;
         __syncthreads();   // warp_sums / list_base / grp_nmin are reused by the next column group

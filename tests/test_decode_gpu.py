@@ -354,3 +354,26 @@ def test_error_paths_report_status_and_message(cuda_device):
     got = fast.decode_device(*heads, K=50).cpu().numpy()
     want = O.decode(*[t.cpu().clone() for t in heads], K=50).numpy()
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_decode_with_nan_and_inf_cells(cuda_device):
+    """NaN / +inf / -inf in the heat map (evaluation_utils.py:21-26 semantics: NaN propagates through
+    max_pool2d, `-inf * 0` is NaN) — tiles holding such values take the scalar walker, the other tiles of
+    the same frame the 4x4-cells-per-thread one; both must agree with the reference's torch ops.  NaN
+    scores rank first in torch.topk in an unspecified order, so those rows are compared as a set."""
+    heads = list(O.synth_heads(44, B=3, tie_free=True))
+    hm = heads[0]
+    hm[0, 0, 20, 20] = float("nan")          # slab 1
+    hm[0, 2, 100, 7] = float("nan")          # slab 6, another class
+    hm[0, 1, 60, 151] = float("inf")         # right edge
+    hm[0, 1, 130, 0] = float("-inf")         # under larger neighbours -> -inf * 0 = NaN
+    hm[1, 0, 0, 0] = float("inf")            # corner; frame 2 stays ordinary
+    want = O.decode(*[t.clone() for t in heads], K=50).numpy()
+    got = _ev().decode(*_cuda(heads, cuda_device), K=50).cpu().numpy()
+    for b in range(3):
+        w_nan, g_nan = np.isnan(want[b, :, 0]), np.isnan(got[b, :, 0])
+        assert w_nan.sum() == g_nan.sum() == (3 if b == 0 else 0)
+        assert np.array_equal(_bits(got[b][~g_nan]), _bits(want[b][~w_nan])), b
+        key = lambda rows: rows[np.lexsort((rows[:, 2], rows[:, 1], rows[:, 9]))][:, 1:]
+        assert np.array_equal(key(got[b][g_nan]), key(want[b][w_nan]))
+    assert np.isinf(got[0, 3, 0]) and np.isinf(got[1, 0, 0])
