@@ -178,3 +178,43 @@ def test_argument_errors(mods):
     rc = lib.load().sfa_bvfeature_rasterize(ctypes.c_void_p(out.data_ptr()), None, 1, 0, ctypes.byref(p),
                                             ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(rast.ws.data_ptr()), 0, None)
     assert rc == -2
+
+
+def test_random_geometries_and_layouts(mods):
+    """30 random makeBVFeature geometries (cell size, asymmetric ranges, map sizes from a few cells to
+    ~0.5 M cells, 3 / 4 / 5 floats per point) on random sweeps that partly leave the boundary: exercises
+    band plans with a partial last band, maps too small / too odd for the tiled path (global-atomic
+    fallback), and both point-load paths."""
+    fast, mirror = mods
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(4242)
+    tiled = fallback = 0
+    for trial in range(30):
+        disc = float(rng.choice([0.05, 0.1, 0.125, 0.2, 0.25, 0.3, 0.5, 1.0]))
+        sx, sy = float(rng.uniform(6, 90)), float(rng.uniform(6, 90))
+        x0, y0 = float(rng.uniform(-60, 20)), float(rng.uniform(-60, 20))
+        z0, sz = float(rng.uniform(-4, 0)), float(rng.choice([2.0, 4.0, 3.5, 6.0]))
+        bnd = {"minX": x0, "maxX": x0 + sx, "minY": y0, "maxY": y0 + sy, "minZ": z0, "maxZ": z0 + sz}
+        H, W = O.bv_feature_shape(disc, bnd)
+        if H * W > 700000 or H < 1 or W < 1:
+            continue
+        floats = int(rng.choice([3, 4, 4, 4, 5]))
+        n = int(rng.integers(1, 60000))
+        kind = ["uniform", "adversarial", "dark"][trial % 3]
+        pts = O.synth_argoverse_sweep(5000 + trial, n, kind, bnd)
+        if floats == 3:
+            pts = np.ascontiguousarray(pts[:, :3])
+        elif floats == 5:
+            pts = np.concatenate([pts, rng.uniform(0, 1, (n, 1)).astype(np.float32)], axis=1)
+        rast = fast.BvFeatureRasterizer(disc, bnd, point_floats=floats, max_batch=2, max_points=65536, device=dev)
+        both = torch.from_numpy(np.stack([pts, pts[::-1].copy()])).to(dev)       # the reduction is order-independent
+        got = rast(both).cpu().numpy()
+        want = O.makeBVFeature(pts, disc, bnd)
+        assert got.shape[1:] == want.shape == (3, H, W), (trial, H, W)
+        assert np.array_equal(got[0].view(np.uint32), want.view(np.uint32)), (trial, disc, bnd, floats, kind)
+        assert np.array_equal(got[1].view(np.uint32), want.view(np.uint32)), (trial, "reversed")
+        if floats == 4 and (H * W) % 4 == 0 and H * W <= 128 * 5120:
+            tiled += 1
+        else:
+            fallback += 1
+    assert tiled >= 5 and fallback >= 5, (tiled, fallback)
