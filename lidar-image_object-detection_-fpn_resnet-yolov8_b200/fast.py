@@ -33,7 +33,9 @@ class BevRasterizer:
     """Stage A for batches of sweeps resident in HBM (replaces get_filtered_lidar + makeBEVMap,
     data_process/kitti_data_utils.py:228-241 and data_process/kitti_bev_utils.py:22-55)."""
 
-    def __init__(self, geom: BevGeometry, max_batch: int = 64, max_points: int = 131072, device=None):
+    def __init__(self, geom: BevGeometry, max_batch: int = 64, max_points: int = 131072, device=None, share_with=None):
+        """share_with: another BevRasterizer of the same map size, batch and sweep length whose workspace, density
+        table and status word this one reuses (calls on the two must be ordered on one stream)."""
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("BevRasterizer needs a CUDA device (there is no CPU fallback)")
@@ -44,6 +46,13 @@ class BevRasterizer:
         nbytes = self.lib.sfa_bev_workspace_bytes(self.max_batch, self.max_points, ctypes.byref(geom.params))
         if nbytes == 0:
             raise _lib.SfaError(-1, _lib.last_error() or "bad geometry")
+        if share_with is not None:
+            if (share_with._ws_bytes < nbytes or share_with.device != self.device or
+                    not np.array_equal(share_with.geom.lut32, geom.lut32)):
+                raise ValueError("share_with must be a rasterizer on the same device with a workspace at least as large")
+            self.workspace, self._ws_ptr, self._ws_bytes = share_with.workspace, share_with._ws_ptr, share_with._ws_bytes
+            self.lut, self.status = share_with.lut, share_with.status
+            return
         with torch.cuda.device(self.device):
             self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
             off = (-self.workspace.data_ptr()) % 256
@@ -108,9 +117,8 @@ class FrontBackRasterizer:
         from . import geometry
         cnf = kitti_config if cnf is None else cnf
         self.front = BevRasterizer(geometry.from_config(cnf, cnf.boundary), max_batch, max_points, device)
-        self.back = BevRasterizer.__new__(BevRasterizer)
-        self.back.__dict__.update(self.front.__dict__)                      # same workspace, table and status word
-        self.back.geom = geometry.from_config(cnf, cnf.boundary_back)
+        self.back = BevRasterizer(geometry.from_config(cnf, cnf.boundary_back), max_batch, max_points, device,
+                                  share_with=self.front)
 
     def __call__(self, points, offsets, max_points, out=None):
         front_out, back_out = (None, None) if out is None else out
