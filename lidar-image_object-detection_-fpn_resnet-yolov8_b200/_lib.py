@@ -70,6 +70,7 @@ PROTOTYPES = {
     "sfa_bvfeature_workspace_bytes": (sz, [i32, i64, ctypes.POINTER(SfaBvParams)]),
     "sfa_bvfeature_rasterize": (ctypes.c_int, [c_void_p, c_void_p, i32, i64, ctypes.POINTER(SfaBvParams), c_void_p,
                                                c_void_p, sz, c_void_p]),
+    "sfa_real_values": (ctypes.c_int, [c_void_p, c_void_p, i32, f32, f32, f32, f32, f32, f32, f32, c_void_p, c_void_p]),
     "sfa_project_boxes": (ctypes.c_int, [c_void_p, i32, c_void_p, i32, i32, c_void_p, i32, i32, i32, ctypes.c_double,
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sfa_pipeline_create": (c_void_p, [i32, i32, i64, ctypes.POINTER(SfaBevParams), c_void_p, i32, i32, i32, i32]),

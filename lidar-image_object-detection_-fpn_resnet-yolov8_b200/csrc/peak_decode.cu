@@ -625,6 +625,29 @@ nms_kernel(const float* __restrict__ heat, int planes, int h, int w, float* __re
     }
 }
 
+// convert_det_to_real_values, evaluation_utils.py:177-193: one post_processing row (score, x, y, z, h, w, l, yaw
+// in BEV pixels) -> metres in the lidar frame, [cls, x, y, z, h, w, l, yaw]; every step rounds to fp32 like
+// numpy's float32 scalars
+__device__ __forceinline__ void real_values_row(const float* __restrict__ o, float cls, float bsy, float bev_w, float bsx,
+                                                float bev_h, float min_x, float min_y, float min_z, float* __restrict__ r) {
+    r[0] = cls;
+    r[1] = __fadd_rn(__fmul_rn(__fdiv_rn(o[2], bev_h), bsx), min_x);   // x <- y pixel, :185
+    r[2] = __fadd_rn(__fmul_rn(__fdiv_rn(o[1], bev_w), bsy), min_y);   // y <- x pixel, :186
+    r[3] = __fadd_rn(o[3], min_z);                                     // :187
+    r[4] = o[4];
+    r[5] = __fmul_rn(__fdiv_rn(o[5], bev_w), bsy);                     // :188
+    r[6] = __fmul_rn(__fdiv_rn(o[6], bev_h), bsx);                     // :189
+    r[7] = -o[7];                                                      // :184
+}
+
+__global__ void __launch_bounds__(128)
+real_values_kernel(const float* __restrict__ rows, const int32_t* __restrict__ cls, int n, float bsy, float bev_w, float bsx,
+                   float bev_h, float min_x, float min_y, float min_z, float* __restrict__ real) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    real_values_row(rows + (size_t)i * 8, (float)cls[i], bsy, bev_w, bsx, bev_h, min_x, min_y, min_z, real + (size_t)i * 8);
+}
+
 __global__ void __launch_bounds__(128)
 post_process_kernel(const float* __restrict__ det, int n, int num_classes, float down_ratio, float bsy, float bev_w,
                     float bsx, float bev_h, float thresh, float min_x, float min_y, float min_z,
@@ -648,17 +671,7 @@ post_process_kernel(const float* __restrict__ det, int n, int num_classes, float
     cls[i] = c;
     keep[i] = (c >= 0 && score > thresh) ? 1 : 0;            // :134, :152
     if (real) {
-        // convert_det_to_real_values, evaluation_utils.py:177-193: BEV pixels -> metres in the lidar
-        // frame, [cls, x, y, z, h, w, l, yaw]; every step rounds to fp32 like numpy's float32 scalars
-        float* r = real + (size_t)i * 8;
-        r[0] = cf;
-        r[1] = __fadd_rn(__fmul_rn(__fdiv_rn(o[2], bev_h), bsx), min_x);   // x <- y pixel, :185
-        r[2] = __fadd_rn(__fmul_rn(__fdiv_rn(o[1], bev_w), bsy), min_y);   // y <- x pixel, :186
-        r[3] = __fadd_rn(o[3], min_z);                                     // :187
-        r[4] = o[4];
-        r[5] = __fmul_rn(__fdiv_rn(o[5], bev_w), bsy);                     // :188
-        r[6] = __fmul_rn(__fdiv_rn(o[6], bev_h), bsx);                     // :189
-        r[7] = -o[7];                                                      // :184
+        real_values_row(o, cf, bsy, bev_w, bsx, bev_h, min_x, min_y, min_z, real + (size_t)i * 8);
     }
 }
 
@@ -773,6 +786,19 @@ extern "C" int sfa_post_process(const float* det, int32_t B, int32_t K, int32_t 
                post_process_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
                    det, n, num_classes, down_ratio, bound_size_y, bev_width, bound_size_x, bev_height, peak_thresh, min_x,
                    min_y, min_z, out, cls, keep, real));
+    SFA_CUDA_TRY(cudaGetLastError());
+    return SFA_OK;
+}
+
+extern "C" int sfa_real_values(const float* rows, const int32_t* cls, int32_t n, float bound_size_y, float bev_width,
+                               float bound_size_x, float bev_height, float min_x, float min_y, float min_z, float* real,
+                               sfa_stream_t stream) {
+    SFA_REQUIRE(n >= 0, "bad row count %d", n);
+    if (n == 0) return SFA_OK;
+    SFA_REQUIRE(rows && cls && real, "NULL pointer argument");
+    SFA_LAUNCH("real_values", (cudaStream_t)stream,
+               real_values_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+                   rows, cls, n, bound_size_y, bev_width, bound_size_x, bev_height, min_x, min_y, min_z, real));
     SFA_CUDA_TRY(cudaGetLastError());
     return SFA_OK;
 }

@@ -135,25 +135,28 @@ def post_processing(detections, num_classes=3, down_ratio=4, peak_thresh=0.2):
 def convert_det_to_real_values(detections, num_classes=3):
     """BEV-pixel boxes -> metric lidar-frame boxes [cls, x, y, z, h, w, l, yaw] (one row per kept
     detection, classes in order) — evaluation_utils.py:177-193.  `detections` is one sample's dict as
-    returned by post_processing.  Vectorised in float32, which is what numpy's float32 scalars give
-    step by step; the batched device form is fast.post_process_dense(..., real=True)."""
-    f = np.float32
-    out = []
+    returned by post_processing.  Computed by `sfa_real_values` in float32, which is what numpy's float32
+    scalars give step by step; the result is the float64 array the reference builds.  The batched device
+    form is fast.post_process_dense(..., real=True)."""
+    rows, cls = [], []
     for cls_id in range(num_classes):
         d = np.asarray(detections[cls_id], dtype=np.float32).reshape(-1, 8)
-        if d.shape[0] == 0:
-            continue
-        r = np.empty((d.shape[0], 8), dtype=np.float64)
-        r[:, 0] = cls_id
-        r[:, 1] = d[:, 2] / f(cnf.BEV_HEIGHT) * f(cnf.bound_size_x) + f(cnf.boundary["minX"])
-        r[:, 2] = d[:, 1] / f(cnf.BEV_WIDTH) * f(cnf.bound_size_y) + f(cnf.boundary["minY"])
-        r[:, 3] = d[:, 3] + f(cnf.boundary["minZ"])
-        r[:, 4] = d[:, 4]
-        r[:, 5] = d[:, 5] / f(cnf.BEV_WIDTH) * f(cnf.bound_size_y)
-        r[:, 6] = d[:, 6] / f(cnf.BEV_HEIGHT) * f(cnf.bound_size_x)
-        r[:, 7] = -d[:, 7]
-        out.append(r)
-    return np.concatenate(out, 0) if out else np.array([])
+        if d.shape[0]:
+            rows.append(d)
+            cls.append(np.full(d.shape[0], cls_id, dtype=np.int32))
+    if not rows:
+        return np.array([])
+    _need_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    rows_d = torch.from_numpy(np.ascontiguousarray(np.concatenate(rows, 0))).to(dev)
+    cls_d = torch.from_numpy(np.concatenate(cls)).to(dev)
+    real = torch.empty_like(rows_d)
+    b = cnf.boundary
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().sfa_real_values(_p(rows_d), _p(cls_d), rows_d.shape[0], float(cnf.bound_size_y),
+                                               float(cnf.BEV_WIDTH), float(cnf.bound_size_x), float(cnf.BEV_HEIGHT),
+                                               float(b["minX"]), float(b["minY"]), float(b["minZ"]), _p(real), _stream(rows_d)))
+    return real.cpu().numpy().astype(np.float64)
 
 
 def convert_sfa3d_to_2d_boxes(sfa_detections, calib, img_shape, min_confidence=0.3):
