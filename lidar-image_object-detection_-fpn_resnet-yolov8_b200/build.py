@@ -20,7 +20,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
-    "--use_fast_math=false" if False else "-prec-div=true",
+    "-prec-div=true",
     "-prec-sqrt=true", "-ftz=false",
 ]
 
@@ -63,7 +63,7 @@ def build(force=False, verbose=False):
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
-    cmd += ["-lcudart_static" if False else "-cudart=shared"]
+    cmd += ["-cudart=shared"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
