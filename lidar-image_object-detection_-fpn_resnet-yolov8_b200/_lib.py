@@ -19,7 +19,7 @@ class SfaBevParams(ctypes.Structure):
                 ("height", i32), ("width", i32), ("apply_filter", i32), ("algorithm", i32)]
 
 
-BEV_AUTO, BEV_TILED, BEV_GLOBAL_ATOMIC = 0, 1, 2   # enum SfaBevAlgorithm
+BEV_AUTO, BEV_TILED, BEV_GLOBAL_ATOMIC, BEV_TILED_TWO_KERNEL = 0, 1, 2, 3   # enum SfaBevAlgorithm
 
 
 class SfaBvParams(ctypes.Structure):

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libsfa_b200.so")
-SOURCES = ["bev_rasterize.cu", "peak_decode.cu", "box_projection.cu", "point_transform.cu", "lidar_filter.cu", "host_pipeline.cu"]
+SOURCES = ["bev_rasterize.cu", "bev_fused.cu", "peak_decode.cu", "box_projection.cu", "point_transform.cu", "lidar_filter.cu", "host_pipeline.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

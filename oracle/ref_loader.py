@@ -1,8 +1,16 @@
-"""Import the reference's hot-path modules IN PLACE from /root/reference (container only).
+"""Import the reference's own hot-path modules (and its fpn_resnet_18), unmodified.
 
-TEST INFRASTRUCTURE. Used only by tests/golden/make_golden.py to generate the committed
-fixtures and by the (skipped-when-absent) live pinning test. Nothing here is shipped, and
-nothing on the GPU box reads /root/reference.
+TEST INFRASTRUCTURE, like everything under oracle/.  Used by tests/golden/make_golden.py (fixtures), the live
+pinning test, the BASELINE config[2] GPU test (the reference's model between our two stages), and
+bench.py's `--impl reference` / `cpu_baseline` legs.  The product never imports it.
+
+Where the reference comes from, first hit wins:
+  1. $SFA_REFERENCE_ROOT
+  2. /root/reference                      (build container only; read in place)
+  3. <repo>/oracle/_ref/sfa               (git-ignored copy made by install(), i.e. by
+                                           `python oracle/ref_loader.py install` or __graft_entry__.build();
+                                           it travels to the GPU box with the snapshot, /root/reference does not)
+Reference sources are never committed: oracle/_ref/ is in .gitignore (and not in .gpurunignore).
 
 Every reference module runs `while not src_dir.endswith("sfa")` at import
 (data_process/kitti_bev_utils.py:13-15, utils/evaluation_utils.py:11-13,
@@ -16,11 +24,47 @@ import io
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("SFA_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+INSTALLED_ROOT = os.path.join(_HERE, "_ref", "sfa")
+SOURCE_ROOT = "/root/reference"
+_COPIED = ("config", "data_process", "utils", "models", "losses")            # SURVEY.md §9's recipe
+_SCRIPTS = ("test6.py", "argoverse_test.py")                                 # functions are compiled out of these
+
+
+def _has_reference(root):
+    return bool(root) and os.path.isfile(os.path.join(root, "data_process", "kitti_bev_utils.py"))
+
+
+def _find_root():
+    for cand in (os.environ.get("SFA_REFERENCE_ROOT"), SOURCE_ROOT, INSTALLED_ROOT):
+        if _has_reference(cand):
+            return cand
+    return os.environ.get("SFA_REFERENCE_ROOT") or SOURCE_ROOT
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "data_process", "kitti_bev_utils.py"))
+    return _has_reference(REFERENCE_ROOT)
+
+
+def install(force=False) -> bool:
+    """Copy the reference's Python packages for this path into oracle/_ref/sfa (a directory whose name ends in
+    "sfa", which is what the reference's import preamble looks for).  No-op when /root/reference is absent."""
+    import shutil
+    if not _has_reference(SOURCE_ROOT):
+        return _has_reference(INSTALLED_ROOT)
+    if _has_reference(INSTALLED_ROOT) and not force:
+        return True
+    os.makedirs(INSTALLED_ROOT, exist_ok=True)
+    for d in _COPIED:
+        dst = os.path.join(INSTALLED_ROOT, d)
+        shutil.rmtree(dst, ignore_errors=True)
+        shutil.copytree(os.path.join(SOURCE_ROOT, d), dst, ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
+    for f in _SCRIPTS:
+        shutil.copy(os.path.join(SOURCE_ROOT, f), os.path.join(INSTALLED_ROOT, f))
+    return True
 
 
 @contextlib.contextmanager
@@ -127,6 +171,28 @@ def load():
     return ns
 
 
+def create_model(arch="fpn_resnet_18", seed=0):
+    """The reference's own network (models/model_utils.py:25-43 -> models/fpn_resnet.py:112-263), random init
+    (imagenet_pretrained=False) under torch.manual_seed(seed), eval mode, configured like test.py:58-70.
+    models/fpn_resnet.py:20 imports matplotlib.pyplot and never uses it: an empty stub stands in when absent."""
+    import types
+    import torch
+    load()   # puts the reference root on sys.path with the realpath answer its preamble needs
+    for name in ("matplotlib", "matplotlib.pyplot"):
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except ImportError:
+                sys.modules[name] = types.ModuleType(name)
+    with _virtual_sfa_root(), contextlib.redirect_stdout(io.StringIO()):
+        model_utils = importlib.import_module("models.model_utils")
+        cfg = types.SimpleNamespace(arch=arch, head_conv=64, imagenet_pretrained=False,
+                                    heads={"hm_cen": 3, "cen_offset": 2, "direction": 2, "z_coor": 1, "dim": 3})
+        torch.manual_seed(seed)
+        model = model_utils.create_model(cfg)
+    return model.eval()
+
+
 @contextlib.contextmanager
 def patched_geometry(ns, boundary, bev_h, bev_w, discretization):
     """Monkey-patch the reference's module-global geometry (config/kitti_config.py:23-47) — the
@@ -144,3 +210,9 @@ def patched_geometry(ns, boundary, bev_h, bev_w, discretization):
     finally:
         (cnf.boundary, cnf.BEV_HEIGHT, cnf.BEV_WIDTH, cnf.DISCRETIZATION,
          cnf.bound_size_x, cnf.bound_size_y, cnf.bound_size_z) = saved
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "install":
+        ok = install(force="--force" in sys.argv)
+        print("reference %s at %s" % ("installed" if ok else "NOT available", INSTALLED_ROOT))

@@ -3,7 +3,7 @@
     python tests/golden/make_golden.py          (build container only: needs /root/reference)
 
 TEST INFRASTRUCTURE.  The reference ships no tests or golden vectors for this path,
-so the pin is: the reference's unmodified functions (imported in place by ref_loader.py) executed on
+so the pin is: the reference's unmodified functions (imported in place by oracle/ref_loader.py) executed on
 seeded synthetic inputs, outputs stored here.  Nothing reads /root/reference at test time.
 
   bev_small.npz      explicit inputs + sparse reference outputs (float64 map, filtered sweep) for

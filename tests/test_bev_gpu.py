@@ -14,8 +14,10 @@ pytestmark = pytest.mark.gpu
 KINDS = ["uniform", "outside", "zties", "gridaligned", "bounds", "nonfinite", "onecell", "clustered"]
 
 
-AUTO, TILED, ATOMIC = 0, 1, 2   # enum SfaBevAlgorithm (include/sfa_b200.h)
-ALGOS = [pytest.param(TILED, id="tiled"), pytest.param(ATOMIC, id="atomic")]
+AUTO, TILED, ATOMIC, TWO_KERNEL = 0, 1, 2, 3   # enum SfaBevAlgorithm (include/sfa_b200.h)
+# tiled = the single persistent bin+band kernel (bev_fused); two_kernel = the same algorithm as bev_bin + bev_band launches
+ALGOS = [pytest.param(TILED, id="tiled"), pytest.param(TWO_KERNEL, id="two_kernel"), pytest.param(ATOMIC, id="atomic")]
+TILED_ALGOS = [pytest.param(TILED, id="tiled"), pytest.param(TWO_KERNEL, id="two_kernel")]
 
 
 def _geom(ogeom, apply_filter=True, algorithm=AUTO):
@@ -58,6 +60,31 @@ def test_bev_single_sweep_bit_exact(cuda_device, kind, n, algorithm):
     want = O.make_bev_scatter(sweep, O.KITTI, True, np.float32)
     _assert_bit_exact(got[0], want, "%s n=%d" % (kind, n))
     assert rast.out_of_map_points() == 0
+
+
+@pytest.mark.parametrize("algorithm", ALGOS)
+def test_bev_reference_fixture_hashes(cuda_device, algorithm):
+    """One hop from the CUDA map to the REFERENCE: sha256 of the GPU output against tests/golden/bev_hashes.json, the
+    hashes of the unmodified reference's makeBEVMap output (.astype(float32)) on the same seeded full-size sweeps
+    (120k KITTI / 250k Argoverse range; written by tests/golden/make_golden.py, which imports the reference)."""
+    import hashlib
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "bev_hashes.json")) as f:
+        cases = json.load(f)
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    geoms = {"kitti": O.KITTI, "kitti_back": O.KITTI_BACK, "argoverse": O.ARGOVERSE}
+    checked = 0
+    for c in cases:
+        geom = geoms[c["geom"]]
+        sweep = O.synth_sweep(c["seed"], c["n"], geom, c["kind"])
+        if sha(sweep) != c["input_sha256"]:
+            continue   # numpy's generator changed since the fixture was made: nothing to compare with
+        got, _ = _run_batch(cuda_device, [sweep], geom, algorithm=algorithm)
+        assert sha(got[0]) == c["bev_f32_sha256"], (c["geom"], c["kind"], c["n"])
+        assert int(np.count_nonzero(got[0][2])) == c["occupied"]
+        checked += 1
+    assert checked >= 12
 
 
 def test_bev_matches_lexsort_formulation(cuda_device):
@@ -167,7 +194,8 @@ def test_bev_max_height_not_a_power_of_two(cuda_device, algorithm):
     _assert_bit_exact(got[0], ref.astype(np.float32), "max_h=3 vs lexsort port")
 
 
-def test_bev_bucket_overflow_paths(cuda_device):
+@pytest.mark.parametrize("algorithm", TILED_ALGOS)
+def test_bev_bucket_overflow_paths(cuda_device, algorithm):
     """A band's bucket holds 8x the even share of a sweep; what does not fit goes to the frame's overflow list.
     Sweeps concentrated in one band / two bands / one cell overflow massively; mixed with ordinary frames in one batch
     (the overflow counters are per ring frame and reset per chunk), run twice on the same workspace."""
@@ -185,12 +213,13 @@ def test_bev_bucket_overflow_paths(cuda_device):
               strip(120000, 0.0, 6.0, zq=2),                               # 8 bands, each about at its bucket's capacity
               O.synth_sweep(903, 50000, O.KITTI, "zties")]
     for attempt in range(2):
-        got, _ = _run_batch(cuda_device, sweeps, O.KITTI, algorithm=TILED)
+        got, _ = _run_batch(cuda_device, sweeps, O.KITTI, algorithm=algorithm)
         for i, s in enumerate(sweeps):
             _assert_bit_exact(got[i], O.make_bev_scatter(s, O.KITTI, True, np.float32), "overflow frame %d" % i)
 
 
-def test_bev_crowded_band_streams_records(cuda_device):
+@pytest.mark.parametrize("algorithm", TILED_ALGOS)
+def test_bev_crowded_band_streams_records(cuda_device, algorithm):
     """More records in one band than its threads hold in registers (8 x 512): the band kernel
     re-reads them from L2 once per phase.  Also a single cell holding > 63 points (LUT saturation)."""
     rng = np.random.default_rng(3)
@@ -200,7 +229,7 @@ def test_bev_crowded_band_streams_records(cuda_device):
                       np.round(rng.uniform(b["minZ"], b["maxZ"], n) * 16) / 16, rng.uniform(0, 1, n)], 1).astype(np.float32)
     sweep[:500, 0] = 10.3
     sweep[:500, 1] = 3.21
-    got, _ = _run_batch(cuda_device, [sweep], O.KITTI, algorithm=TILED)
+    got, _ = _run_batch(cuda_device, [sweep], O.KITTI, algorithm=algorithm)
     _assert_bit_exact(got[0], O.make_bev_scatter(sweep, O.KITTI, True, np.float32), "crowded band")
 
 
@@ -212,11 +241,11 @@ def test_bev_negative_zero_and_nan_payload_bits(cuda_device):
     sweep[:, 1] = 0.5
     sweep[:, 2] = [-0.0, 0.0, 0.0, -0.0, -1.0, -0.0]
     sweep[:, 3] = [0.1, 0.2, 0.3, 0.4, 0.5, 0.6]
-    for algorithm in (TILED, ATOMIC):
+    for algorithm in (TILED, TWO_KERNEL, ATOMIC):
         got, _ = _run_batch(cuda_device, [sweep], O.KITTI, apply_filter=False, algorithm=algorithm)
         want = O.makeBEVMap(sweep, O.KITTI.boundary, O.KITTI).astype(np.float32)
         assert np.array_equal(got[0], want)
-        if algorithm == TILED:   # the tiled path also keeps the sign bit of a zero winner
+        if algorithm != ATOMIC:   # the tiled path also keeps the sign bit of a zero winner
             _assert_bit_exact(got[0], want, "signed zero")
 
 

@@ -1,5 +1,5 @@
 """CPU, build container only: re-run the oracle against the REFERENCE's own functions live
-(imported in place from /root/reference by tests/golden/ref_loader.py).  Skipped wherever the
+(imported in place from /root/reference by oracle/ref_loader.py).  Skipped wherever the
 reference is absent (e.g. on the GPU box) — the committed fixtures cover that case."""
 import numpy as np
 import pytest
