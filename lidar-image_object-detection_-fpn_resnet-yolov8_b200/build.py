@@ -36,7 +36,10 @@ STAMP = LIB + ".flags"   # the variant (release / SFA_DEBUG_TIMING) the library 
 
 
 def _variant():
-    return "debug-timing" if os.environ.get("SFA_DEBUG_TIMING") == "1" else "release"
+    # SFA_NVCC_DEFS: extra -D flags for kernel experiments (e.g. "-DSFA_FUSED_WORKERS=224"); part of the stamp
+    base = "debug-timing" if os.environ.get("SFA_DEBUG_TIMING") == "1" else "release"
+    extra = os.environ.get("SFA_NVCC_DEFS", "").strip()
+    return base + (" " + extra if extra else "")
 
 
 def _stale():
@@ -60,6 +63,7 @@ def build(force=False, verbose=False):
     cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-shared", "-o", LIB]
     if os.environ.get("SFA_DEBUG_TIMING") == "1":   # developer aid: per-phase cycle counters in bev_band
         cmd += ["-DSFA_DEBUG_TIMING"]
+    cmd += os.environ.get("SFA_NVCC_DEFS", "").split()
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]

@@ -26,9 +26,13 @@
 namespace sfa {
 namespace {
 
-constexpr int kFusedThreads = 256;
-constexpr int kFusedPoints = 4;                               // points per thread of a bin tile
-constexpr int kFusedTile = kFusedThreads * kFusedPoints;      // 1024
+#ifndef SFA_FUSED_WORKERS
+#define SFA_FUSED_WORKERS 224
+#endif
+constexpr int kFusedWorkers = SFA_FUSED_WORKERS;              // threads that do the arithmetic (multiple of 32, >= 128)
+constexpr int kFusedThreads = kFusedWorkers + 32;             // + the service warp (one active thread)
+constexpr int kFusedPoints = 4;                               // points per worker of a bin tile
+constexpr int kFusedTile = kFusedWorkers * kFusedPoints;      // 1024
 constexpr int kFusedBands = 128;
 constexpr int kFusedCtasPerSm = 4;
 constexpr int kFusedMaxRing = 32;
@@ -40,12 +44,12 @@ constexpr int kCtlLine = 32;                                   // uint32 per lin
 constexpr size_t kFusedCtlOffset = 256;
 constexpr int kCtlTicket = 0;
 constexpr int kCtlTilesDone = 1;                               // + ring slot
-constexpr int kCtlBandsPre = 1 + kFusedMaxRing;
-constexpr int kCtlBandsDone = 1 + 2 * kFusedMaxRing;
-constexpr int kCtlOvf = 1 + 3 * kFusedMaxRing;
+constexpr int kCtlBandsDone = 1 + kFusedMaxRing;
+constexpr int kCtlOvf = 1 + 2 * kFusedMaxRing;                 // two per ring slot (+ kFusedMaxRing for odd uses)
 constexpr int kCtlTimeouts = 1 + 4 * kFusedMaxRing;
 constexpr size_t kFusedCtlBytes = (size_t)(2 + 4 * kFusedMaxRing) * kCtlLine * sizeof(uint32_t);
 constexpr size_t kFusedZerosOffset = 24576;
+static_assert(kFusedWorkers >= kFusedBands && kFusedWorkers % 32 == 0, "one scan thread per band");
 static_assert(kFusedCtlOffset + kFusedCtlBytes <= kFusedZerosOffset, "control block overlaps the zero block");
 static_assert(kFusedZerosOffset + 3 * (size_t)kMaxCellsPerBand * sizeof(uint32_t) <= kHeaderBytes, "zero block does not fit the header");
 
@@ -80,17 +84,6 @@ __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {
     asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
-// Bounded: a dependency that does not resolve within ~1 s (a bug, never observed) is recorded in the control
-// block's timeout word — sfa_bev_rasterize's caller sees wrong maps, not a hung GPU.
-__device__ __forceinline__ void spin_until_ge(const uint32_t* p, uint32_t target, uint32_t* timeouts) {
-    for (uint32_t spins = 0; ld_acquire_u32(p) < target; ++spins) {
-        __nanosleep(128);
-        if (spins > (1u << 22)) {
-            atomicAdd(timeouts, 1u);
-            return;
-        }
-    }
-}
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(count) : "memory");
 }
@@ -102,11 +95,24 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
-        "}\n" ::"r"(smem_addr_u32(bar)), "r"(parity)
+        "}\n" ::"r"(smem_addr_u32(bar)), "r"(parity), "r"(200u)
+        : "memory");
+}
+// the service thread's wait: the hardware may suspend the thread for up to ~1 us per probe instead of spinning
+__device__ __forceinline__ void mbar_wait_relaxed(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITR_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONER_%=;\n"
+        "bra WAITR_%=;\n"
+        "DONER_%=:\n"
+        "}\n" ::"r"(smem_addr_u32(bar)), "r"(parity), "r"(1000u)
         : "memory");
 }
 // global -> shared::cta bulk copy, completion (bytes) on an mbarrier of this CTA
@@ -116,35 +122,70 @@ __device__ __forceinline__ void bulk_load_g2s(void* sdst, const void* gsrc, uint
                  : "memory");
 }
 
-// ticket -> (role, frame, index); see the file header for the order
-__device__ __forceinline__ void decode_ticket(uint32_t t, const FusedArgs& a, int& role, int& frame, int& idx) {
+// Ticket t = (step s = t / P, k = t % P), P = max(tiles per frame, bands per frame): the bin tile k of frame s (if any)
+// and then the band k of frame s - LAG (if any).  A CTA therefore alternates bin tile / band item: the TMA drain and
+// zero-fill of a band's planes hide behind the next bin tile.
+struct Work { int role, frame, idx; };
+__device__ __forceinline__ int decode_ticket(uint32_t t, const FusedArgs& a, Work* w) {
     const uint32_t tb = (uint32_t)a.tb, nb = (uint32_t)a.plan.nb, nf = (uint32_t)a.nf;
-    const uint32_t lag = min((uint32_t)a.lag, nf);
-    const uint32_t n1 = lag * tb, per = tb + nb, n2 = (nf - lag) * per;
-    if (t < n1) {
-        role = kRoleBin; frame = (int)(t / tb); idx = (int)(t - (uint32_t)frame * tb);
-    } else if (t < n1 + n2) {
-        const uint32_t u = t - n1, s = u / per, r = u - s * per;
-        if (r < tb) { role = kRoleBin; frame = (int)(lag + s); idx = (int)r; }
-        else        { role = kRoleBand; frame = (int)s; idx = (int)(r - tb); }
-    } else if (t < nf * per) {
-        const uint32_t u = t - n1 - n2, s = u / nb;
-        role = kRoleBand; frame = (int)(nf - lag + s); idx = (int)(u - s * nb);
-    } else {
-        role = kRoleDone; frame = 0; idx = 0;
+    const uint32_t per = max(tb, nb), lag = (uint32_t)a.lag;
+    const uint32_t s = t / per, k = t - s * per;
+    int n = 0;
+    if (s >= nf + lag) {
+        w[0].role = kRoleDone; w[0].frame = 0; w[0].idx = 0;
+        return 1;
     }
+    if (s < nf && k < tb) { w[n].role = kRoleBin; w[n].frame = (int)s; w[n].idx = (int)k; ++n; }
+    if (s >= lag && k < nb) { w[n].role = kRoleBand; w[n].frame = (int)(s - lag); w[n].idx = (int)k; ++n; }
+    return n;   // may be 0: the ticket holds nothing (first / last LAG steps of the shorter kind)
 }
 
+struct __align__(16) FusedItem {   // what the service thread publishes for the workers
+    int role;
+    int idx;                    // bin: tile index inside its sweep; band: band index
+    uint32_t aux;               // bin: points in the tile
+    int slot;                   // ring slot of the item's frame
+    unsigned long long ptr;     // bin: first point of the tile; band: the band's bucket (its cursor: slot, idx)
+    unsigned long long out;     // the frame's overflow counter (control block)
+};
+
+__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kFusedWorkers) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_addr_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+// The kernel.  Threads 0 .. kFusedWorkers-1 are WORKERS (all the arithmetic); lane 0 of the last warp is the SERVICE
+// thread: it claims tickets, waits for an item's dependencies, publishes the item (pointers, counts) one item ahead of
+// the workers, and after the workers are done with an item performs its tail — release fence + completion signal,
+// the TMA stores of a band's planes, the wait for the drain, and the TMA zero-fills — so none of those round trips
+// sits between two items of the workers.
+//   item_full[b]  service -> workers: s_item[b] is valid            (count 1)
+//   tail_bar[b]   workers -> service: the item of buffer b is done   (count kFusedWorkers)
+//   zero_bar      TMA -> workers: the planes are zero again            (transaction bytes)
 template <bool FILTER, bool RANGE_SAFE, bool MUL_HEIGHT>
 __global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm)
 bev_fused_kernel(const __grid_constant__ FusedArgs a) {
     extern __shared__ __align__(128) uint32_t fsm[];
-    __shared__ uint32_t hist[kFusedBands];   // bin: points of this tile per band
+    __shared__ uint32_t hist[kFusedBands];   // bin: points of this tile per band (zero between tiles)
     __shared__ uint32_t soff[kFusedBands];   // bin: exclusive scan of hist
     __shared__ uint32_t gpos[kFusedBands];   // bin: run's first position in the band's bucket minus its first stage slot
     __shared__ float lut[64];
-    __shared__ int s_item[2][4];             // double-buffered work item: role, frame, idx, ready
-    __shared__ __align__(8) unsigned long long zero_bar[2];   // [0] planes, [1] inv / stage region
+    __shared__ uint32_t s_nkept, wsum[kFusedBands / 32];
+    __shared__ FusedItem s_item[2];
+    __shared__ __align__(8) unsigned long long item_full[2], tail_bar[2], zero_bar;
 
     const int cpb = a.plan.cpb, nb = a.plan.nb;
     uint32_t* const inten = fsm;             // the three planes are contiguous: one zero-fill, and they leave as they are
@@ -153,104 +194,183 @@ bev_fused_kernel(const __grid_constant__ FusedArgs a) {
     uint32_t* const inv = fsm + 3 * cpb;     // phase 2: max of ~index among the max-z points; idle state 0
     uint4* const stage = reinterpret_cast<uint4*>(inv);   // bin tile: records sorted by band (aliases inv)
     const int tid = threadIdx.x;
+    const uint32_t inv_bytes = (uint32_t)max((size_t)cpb * 4, kFusedStageBytes);
+
+    // ---- prologue (all threads) ----
+    if (tid == 0) {
+        mbar_init(&item_full[0], 1); mbar_init(&item_full[1], 1);
+        mbar_init(&tail_bar[0], kFusedWorkers); mbar_init(&tail_bar[1], kFusedWorkers);
+        mbar_init(&zero_bar, 1);
+    }
+    if (tid < 64) lut[tid] = a.lut[tid];
+    if (tid < kFusedBands) hist[tid] = 0;
+    for (uint32_t i = tid; i < (3u * cpb * 4u + inv_bytes) / 16; i += kFusedThreads) reinterpret_cast<uint4*>(fsm)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();   // mbarrier init + the generic-proxy zero fill, before any bulk copy touches them
+    __syncthreads();
+
+    if (tid >= kFusedWorkers) {
+        // =========================================== SERVICE thread ===========================================
+        if (tid != kFusedWorkers) return;
+        auto ctl = [&](int what, int slot) { return a.ctl + (what + slot) * kCtlLine; };
+        // tickets are claimed one ahead (the atomic's round trip overlaps the current iteration); a ticket yields 0-2 items
+        Work fifo[2];
+        int fifo_n = 0, fifo_at = 0;
+        uint32_t t_ahead = atomicAdd(a.ctl + kCtlTicket * kCtlLine, 1u);
+        auto claim = [&]() {
+            while (fifo_at == fifo_n) {   // (an empty ticket: take the next one at once)
+                fifo_n = decode_ticket(t_ahead, a, fifo);
+                fifo_at = 0;
+                if (fifo_n == 0) t_ahead = atomicAdd(a.ctl + kCtlTicket * kCtlLine, 1u);
+            }
+            const Work w = fifo[fifo_at++];
+            // the next ticket is claimed when the last item of this one is handed out: its round trip hides behind that item
+            if (fifo_at == fifo_n && w.role != kRoleDone) t_ahead = atomicAdd(a.ctl + kCtlTicket * kCtlLine, 1u);
+            return w;
+        };
+        auto deps_ready = [&](const Work& w) -> bool {
+            const int slot = w.frame % a.ring;
+            const uint32_t use = (uint32_t)(w.frame / a.ring);
+            if (w.role == kRoleBin) return use == 0 || ld_acquire_u32(ctl(kCtlBandsDone, slot)) >= use * (uint32_t)nb;
+            if (w.role == kRoleBand) return ld_acquire_u32(ctl(kCtlTilesDone, slot)) >= (use + 1u) * (uint32_t)a.tb;
+            return true;
+        };
+        auto wait_deps = [&](const Work& w) {
+            for (uint32_t spins = 0; !deps_ready(w); ++spins) {
+                __nanosleep(100);
+                if (spins > (1u << 22)) {   // ~1 s: a bug, never observed; recorded instead of hanging the GPU
+                    atomicAdd(ctl(kCtlTimeouts, 0), 1u);
+                    return;
+                }
+            }
+        };
+        const size_t cells = (size_t)a.g.H * a.g.W;
+        auto publish = [&](const Work& w, int buf) {
+            FusedItem it;
+            it.role = w.role; it.idx = w.idx; it.aux = 0; it.slot = w.frame % a.ring; it.ptr = 0; it.out = 0;
+            if (w.role == kRoleBin) {
+                // overflow counters alternate with the use parity of the ring slot; tile 0 of use u zeroes the one use
+                // u + 1 will append to (its previous user, use u - 1, is done: that was this tile's dependency), and the
+                // store is released by this tile's own completion signal, long before any tile of use u + 1 starts
+                if (w.idx == 0) *reinterpret_cast<volatile uint32_t*>(ctl(kCtlOvf + kFusedMaxRing * (int)(((w.frame / a.ring) + 1) & 1), it.slot)) = 0;
+                it.out = (unsigned long long)ctl(kCtlOvf + kFusedMaxRing * (int)((w.frame / a.ring) & 1), it.slot);
+                int64_t start, n;
+                sweep_range(a.offsets, w.frame, a.max_points, start, n);
+                const int64_t first = (int64_t)w.idx * kFusedTile;
+                it.aux = (uint32_t)max((int64_t)0, min((int64_t)kFusedTile, n - first));
+                it.ptr = (unsigned long long)(a.pts + start + first);
+            } else if (w.role == kRoleBand) {
+                it.ptr = (unsigned long long)(a.buckets + (size_t)it.slot * a.slot_recs + (size_t)w.idx * a.bucket_cap);
+                it.out = (unsigned long long)ctl(kCtlOvf + kFusedMaxRing * (int)((w.frame / a.ring) & 1), it.slot);
+            }
+            s_item[buf] = it;
+            mbar_arrive(&item_full[buf]);   // release: the item, then the flag
+        };
+        uint32_t plane_fills = 0;
+        auto tail = [&](const Work& w) {
+            const int slot = w.frame % a.ring;
+            if (w.role == kRoleBin) {
+                __threadfence();                      // release: the workers' record stores, then the signal
+                atomicAdd(ctl(kCtlTilesDone, slot), 1u);
+            } else {
+                // the three shared arrays ARE the band's planes (empty cells kept their zero fill; channel 0
+                // intensity, 1 height, 2 density, kitti_bev_utils.py:50-53)
+                const size_t cell0 = (size_t)w.idx * cpb;
+                const uint32_t bytes = (uint32_t)(min((size_t)cpb, cells - cell0) * sizeof(float));
+                float* const o = a.out + (size_t)w.frame * 3 * cells + cell0;
+                const unsigned long long pol = l2_evict_first_policy();
+                bulk_store_s2g_hint(o, inten, bytes, pol);
+                bulk_store_s2g_hint(o + cells, zkey, bytes, pol);
+                bulk_store_s2g_hint(o + 2 * cells, cnt, bytes, pol);
+                bulk_commit_group();
+                // while the TMA drains the planes: cursor back to zero for the slot's next frame, then the completion signal
+                *reinterpret_cast<volatile uint32_t*>(a.cursors + ((size_t)slot * nb + w.idx) * kCursorStride) = 0;
+                __threadfence();
+                atomicAdd(ctl(kCtlBandsDone, slot), 1u);
+                bulk_wait_group_read0();    // the planes have left shared memory ...
+                mbar_expect_tx(&zero_bar, 3u * (uint32_t)cpb * 4u);
+                bulk_load_g2s(inten, a.zeros, 3u * (uint32_t)cpb * 4u, &zero_bar);   // ... and are zero-filled for the next band item
+                ++plane_fills;
+            }
+        };
+        Work cur = claim();
+        wait_deps(cur);
+        publish(cur, 0);
+        for (uint32_t i = 0; cur.role != kRoleDone; ++i) {
+            const Work nxt = claim();
+            // publish the next item EARLY when its dependencies already hold (buffer (i+1)&1 is free: the workers arrived
+            // for item i-1 before the previous iteration's tail); never spin before this CTA's own tail is out
+            bool published = false;
+            if (deps_ready(nxt)) { publish(nxt, (int)((i + 1) & 1u)); published = true; }
+            mbar_wait_relaxed(&tail_bar[i & 1u], (i >> 1) & 1u);
+            tail(cur);
+            if (!published) { wait_deps(nxt); publish(nxt, (int)((i + 1) & 1u)); }
+            cur = nxt;
+        }
+        bulk_wait_group0();   // all plane stores performed before the CTA retires
+        if (plane_fills) mbar_wait(&zero_bar, (plane_fills - 1u) & 1u);   // the last zero-fill targets this CTA's shared memory
+        return;
+    }
+
+    // ================================================ WORKERS ================================================
     auto height = [&](uint32_t zbits) -> float {   // kitti_bev_utils.py:44 (fp32 division)
         return MUL_HEIGHT ? __fmul_rn(__uint_as_float(zbits), a.inv_h) : __fdiv_rn(__uint_as_float(zbits), a.g.max_h);
     };
-    auto ctl = [&](int what, int slot) { return a.ctl + (what + slot) * kCtlLine; };
-    auto inv_words = [&]() { return (uint32_t)max((size_t)cpb, kFusedStageBytes / 4); };
-
-    // ---- state carried from one loop iteration to the next ----
-    // st bit 0: which s_item buffer holds the CURRENT item; 1: planes zero-fill not yet waited for; 2: same for the
-    // inv / stage region; 3, 4: parity of the next completion of zero_bar[0] / [1]
+    // st bit 1: a planes zero-fill has not been waited for; bit 3: parity of the next completion of zero_bar;
+    // bit 5: this thread has issued the current item's first loads already
     uint32_t st = 0;
     uint4 pre[kFusedSpecRecords];   // bin: the thread's 4 points; band: its first 4 records
-    uint32_t aux = 0;               // bin: points in the tile; band: the cursor (record count), loaded with the records
+    uint32_t n_all_pre = 0;         // band: the record count, loaded with them
     uint32_t n_oob_total = 0;
-
-    // Thread 0: turn a claimed ticket into work item `buf` (+ whether a band item's records are already complete).
-    auto publish = [&](uint32_t t, int buf) {
-        int r, f, i, rdy = 1;
-        decode_ticket(t, a, r, f, i);
-        if (r == kRoleBand)
-            rdy = ld_acquire_u32(ctl(kCtlTilesDone, f % a.ring)) >= (uint32_t)(f / a.ring + 1) * (uint32_t)a.tb;
-        s_item[buf][0] = r; s_item[buf][1] = f; s_item[buf][2] = i; s_item[buf][3] = rdy;
-    };
-    auto bucket_of = [&](int f, int b) -> const BevRecord* {
-        return a.buckets + (size_t)(f % a.ring) * a.slot_recs + (size_t)b * a.bucket_cap;
-    };
-    auto cursor_of = [&](int f, int b) -> uint32_t* {
-        return a.cursors + ((size_t)(f % a.ring) * nb + b) * kCursorStride;
-    };
-    auto load_band_head = [&](int f, int b) {   // cursor + the first records of every thread (a bucket is bucket_cap records of mapped memory)
-        const BevRecord* rec = bucket_of(f, b);
-        aux = ld_cg_u32(cursor_of(f, b));
-#pragma unroll
-        for (int j = 0; j < kFusedSpecRecords; ++j) {
-            const uint32_t i = tid + j * kFusedThreads;
-            pre[j] = (i < a.bucket_cap) ? ld_record(rec + i) : make_uint4(0, 0, 0, 0);
+    auto wait_zero = [&]() {
+        if (st & 2u) {
+            mbar_wait(&zero_bar, (st >> 3) & 1u);
+            st ^= 8u;
+            st &= ~2u;
         }
     };
-    // Issue the first loads of work item `buf` (valid after a barrier that follows its publish).
-    auto prefetch_item = [&](int buf) {
-        const int r = s_item[buf][0], f = s_item[buf][1], i = s_item[buf][2];
-        if (r == kRoleBin) {
-            int64_t start, n;
-            sweep_range(a.offsets, f, a.max_points, start, n);
-            const int64_t first = (int64_t)i * kFusedTile;
-            const int n_tile = (int)max((int64_t)0, min((int64_t)kFusedTile, n - first));
-            aux = (uint32_t)n_tile;
-            const float4* tile = a.pts + start + first;
+    auto first_loads = [&](const FusedItem& it) {
+        if (it.role == kRoleBin) {
+            const float4* tile = reinterpret_cast<const float4*>(it.ptr);
             const unsigned long long pol = l2_evict_first_policy();
 #pragma unroll
             for (int j = 0; j < kFusedPoints; ++j) {
-                if (tid + kFusedThreads * j < n_tile) {
-                    const float4 p = ld_stream_f4_evict_first(tile + tid + kFusedThreads * j, pol);
+                if (tid + kFusedWorkers * j < (int)it.aux) {
+                    const float4 p = ld_stream_f4_evict_first(tile + tid + kFusedWorkers * j, pol);
                     pre[j] = make_uint4(__float_as_uint(p.x), __float_as_uint(p.y), __float_as_uint(p.z), __float_as_uint(p.w));
                 }
             }
-        } else if (r == kRoleBand && s_item[buf][3]) {
-            load_band_head(f, i);
+        } else if (it.role == kRoleBand) {   // the cursor (final: all the frame's tiles have signalled) and, before its value
+            // is known, the first records of every thread (a bucket is bucket_cap records of mapped memory)
+            const BevRecord* rec = reinterpret_cast<const BevRecord*>(it.ptr);
+            n_all_pre = ld_cg_u32(a.cursors + ((size_t)it.slot * nb + it.idx) * kCursorStride);
+#pragma unroll
+            for (int j = 0; j < kFusedSpecRecords; ++j) {
+                const uint32_t i = tid + j * kFusedWorkers;
+                pre[j] = (i < a.bucket_cap) ? ld_record(rec + i) : make_uint4(0, 0, 0, 0);
+            }
         }
     };
-    auto wait_zero = [&](int which) {   // which: 0 planes, 1 inv / stage region
-        if (st & (2u << which)) {
-            mbar_wait(&zero_bar[which], (st >> (3 + which)) & 1u);
-            st ^= 8u << which;
-            st &= ~(2u << which);
+    // the next item's first loads, if the service thread has published it already (it usually has)
+    auto prefetch_next = [&](uint32_t i) {
+        const uint32_t nb_ = (i + 1u) & 1u;
+        if (mbar_test(&item_full[nb_], ((i + 1u) >> 1) & 1u)) {
+            first_loads(s_item[nb_]);
+            st |= 32u;
         }
     };
 
-    // ---- prologue ----
-    if (tid == 0) {
-        mbar_init(&zero_bar[0], 1);
-        mbar_init(&zero_bar[1], 1);
-        publish(atomicAdd(a.ctl + kCtlTicket * kCtlLine, 1u), 0);
-    }
-    if (tid < 64) lut[tid] = a.lut[tid];
-    for (uint32_t i = tid; i < (3u * cpb + inv_words()) / 4; i += kFusedThreads) reinterpret_cast<uint4*>(fsm)[i] = make_uint4(0, 0, 0, 0);
-    fence_proxy_async_smem();   // mbarrier init + the generic-proxy zero fill, before any bulk copy touches them
-    __syncthreads();
-    prefetch_item(0);
+    for (uint32_t i = 0;; ++i) {
+        const uint32_t buf = i & 1u;
+        if (!(st & 32u)) mbar_wait(&item_full[buf], (i >> 1) & 1u);
+        const FusedItem it = s_item[buf];
+        if (it.role == kRoleDone) break;
+        if (!(st & 32u)) first_loads(it);
+        st &= ~32u;
 
-    while (true) {
-        const int cur = (int)(st & 1u);
-        const int role = s_item[cur][0];
-        if (role == kRoleDone) break;
-        const int frame = s_item[cur][1], idx = s_item[cur][2];
-        __syncthreads();   // the previous item's shared state is dead; s_item[cur ^ 1] may be overwritten
-        uint32_t t_next = 0;
-        if (tid == 0) t_next = atomicAdd(a.ctl + kCtlTicket * kCtlLine, 1u);   // consumed by publish() further down
-        const int slot = frame % a.ring;
-        const uint32_t use = (uint32_t)(frame / a.ring);   // how many frames used this ring slot before
-
-        if (role == kRoleBin) {
-            // =============================== bin tile (frame, idx) ===============================
+        if (it.role == kRoleBin) {
+            // =============================== bin tile ===============================
             const int lane = tid & 31, warp = tid >> 5;
-            const int n_tile = (int)aux;
-            if (tid < kFusedBands) hist[tid] = 0;
-            wait_zero(1);   // a zero-fill of the staging area may still be landing
-            if (tid == 0 && use > 0) spin_until_ge(ctl(kCtlBandsDone, slot), use * (uint32_t)nb, ctl(kCtlTimeouts, 0));   // ring slot free again
-            __syncthreads();
+            const int n_tile = (int)it.aux;
             // packed per point: band << 24 | rank-in-(tile, band);  0xFFFFFFFF = dropped
             uint32_t packed[kFusedPoints], local[kFusedPoints];
             {
@@ -263,7 +383,7 @@ bev_fused_kernel(const __grid_constant__ FusedArgs a) {
                     float z;
                     bool oob = false;
                     int cell = point_to_cell_fast<FILTER, RANGE_SAFE>(p, a.g, dv, z, oob);
-                    if (tid + kFusedThreads * j >= n_tile) { cell = -1; oob = false; }
+                    if (tid + kFusedWorkers * j >= n_tile) { cell = -1; oob = false; }
                     n_oob += oob ? 1u : 0u;
                     const uint32_t b = band_of((uint32_t)max(cell, 0), a.plan);
                     local[j] = (b << 16) | ((uint32_t)max(cell, 0) - b * (uint32_t)cpb);
@@ -273,58 +393,49 @@ bev_fused_kernel(const __grid_constant__ FusedArgs a) {
                 }
                 if (!RANGE_SAFE) n_oob_total += n_oob;
             }
-            __syncthreads();
-            // warp 0: exclusive scan over the bands -> stage slots, and the reservation of the global runs (atomics only
-            // ISSUED here; their results are consumed after the staging)
-            uint32_t res[kFusedBands / 32], slot0[kFusedBands / 32];
-            if (warp == 0) {
-                uint32_t c[kFusedBands / 32], run = 0;
-#pragma unroll
-                for (int q = 0; q < kFusedBands / 32; ++q) {   // lane owns bands 4*lane .. 4*lane+3
-                    const int b = lane * (kFusedBands / 32) + q;
-                    c[q] = b < nb ? hist[b] : 0u;
-                    run += c[q];
-                }
-                uint32_t incl = run;
+            worker_barrier();
+            // threads 0..127, one band each: exclusive scan over the bands -> stage slots, and the reservation of the global
+            // runs (atomics only ISSUED here; their results are consumed after the staging).  Leaves the histogram zero.
+            uint32_t res = 0, slot0 = 0;
+            if (tid < kFusedBands) {
+                const uint32_t c = hist[tid];
+                hist[tid] = 0;
+                uint32_t incl = c;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
                     if (lane >= d) incl += v;
                 }
-                uint32_t at = incl - run;
-                uint32_t* cursors = a.cursors + (size_t)slot * nb * kCursorStride;
+                if (lane == 31) wsum[warp] = incl;
+                asm volatile("bar.sync 2, %0;" ::"n"(kFusedBands) : "memory");
+                uint32_t base = 0;
 #pragma unroll
-                for (int q = 0; q < kFusedBands / 32; ++q) {
-                    const int b = lane * (kFusedBands / 32) + q;
-                    soff[b] = at;
-                    slot0[q] = at;
-                    at += c[q];
-                    res[q] = c[q] ? atomicAdd(cursors + (size_t)b * kCursorStride, c[q]) : 0u;
-                }
+                for (int q = 0; q < kFusedBands / 32 - 1; ++q) base += (q < warp) ? wsum[q] : 0u;
+                slot0 = base + incl - c;
+                soff[tid] = slot0;
+                if (tid == kFusedBands - 1) s_nkept = base + incl;
+                if (c) res = atomicAdd(a.cursors + ((size_t)it.slot * nb + tid) * kCursorStride, c);
             }
-            __syncthreads();
+            worker_barrier();
             {
-                const uint32_t i0 = (uint32_t)idx * kFusedTile + tid;
+                const uint32_t i0 = (uint32_t)it.idx * kFusedTile + tid;
 #pragma unroll
                 for (int j = 0; j < kFusedPoints; ++j) {
                     if (packed[j] != 0xFFFFFFFFu) {
                         const uint32_t s = soff[packed[j] >> 24] + (packed[j] & 0xFFFFFFu);
-                        stage[s] = make_uint4(pre[j].z, pre[j].w, i0 + kFusedThreads * j, local[j]);
+                        stage[s] = make_uint4(pre[j].z, pre[j].w, i0 + kFusedWorkers * j, local[j]);
                     }
                 }
             }
-            if (warp == 0) {
-#pragma unroll
-                for (int q = 0; q < kFusedBands / 32; ++q) gpos[lane * (kFusedBands / 32) + q] = res[q] - slot0[q];
-            }
-            const int n_kept = (int)(soff[nb - 1] + hist[nb - 1]);   // both final since the barrier above
-            if (tid == 0) publish(t_next, cur ^ 1);
-            __syncthreads();
-            prefetch_item(cur ^ 1);   // the next item's first loads fly during the copy-out
+            if (tid < kFusedBands) gpos[tid] = res - slot0;
+            prefetch_next(i);   // pre[] is free: the next item's first loads fly during the barrier and the copy-out
+            const int n_kept = (int)s_nkept;
+            worker_barrier();
             // copy out in sorted order: stage slot s belongs to band (stage[s].w >> 16), record s - soff[band] of its run
-            BevRecord* fb = a.buckets + (size_t)slot * a.slot_recs;
-            for (int s0 = tid; s0 < n_kept; s0 += kFusedThreads) {
+            BevRecord* fb = a.buckets + (size_t)it.slot * a.slot_recs;
+            for (int s0 = tid; s0 < n_kept; s0 += kFusedWorkers) {
                 uint4 r = stage[s0];
+                stage[s0] = make_uint4(0, 0, 0, 0);   // the staging area doubles as `inv`, whose idle state is zero
                 const uint32_t b = r.w >> 16;
                 const uint32_t pos = gpos[b] + (uint32_t)s0;
                 if (pos < a.bucket_cap) {
@@ -332,61 +443,43 @@ bev_fused_kernel(const __grid_constant__ FusedArgs a) {
                     *reinterpret_cast<uint4*>(fb + (size_t)b * a.bucket_cap + pos) = r;
                 } else {   // the band's bucket is full: frame overflow list, record keeps its band tag
                     BevRecord* ovf = fb + (size_t)nb * a.bucket_cap;
-                    *reinterpret_cast<uint4*>(ovf + atomicAdd(ctl(kCtlOvf, slot), 1u)) = r;
+                    *reinterpret_cast<uint4*>(ovf + atomicAdd(reinterpret_cast<uint32_t*>(it.out), 1u)) = r;
                 }
             }
-            __syncthreads();   // all records of the tile are stored (and the staging area is free)
-            const bool band_next = s_item[cur ^ 1][0] == kRoleBand;
-            if (tid == 0) {
-                __threadfence();                      // release: the CTA's record stores, then the signal
-                atomicAdd(ctl(kCtlTilesDone, slot), 1u);
-                if (band_next) {   // a band item needs `inv` idle (zero) again
-                    fence_proxy_async_smem();
-                    mbar_expect_tx(&zero_bar[1], inv_words() * 4u);
-                    bulk_load_g2s(inv, a.zeros, inv_words() * 4u, &zero_bar[1]);
-                }
-            }
-            if (band_next) st |= 4u;
+            mbar_arrive(&tail_bar[buf]);   // this thread's records are stored, its staging reads done
         } else {
-            // =============================== band item (frame, idx) ===============================
-            const BevRecord* rec = bucket_of(frame, idx);
-            const bool ready = s_item[cur][3] != 0;
-            if (tid == 0 && !ready) spin_until_ge(ctl(kCtlTilesDone, slot), (use + 1u) * (uint32_t)a.tb, ctl(kCtlTimeouts, 0));
-            wait_zero(0);
-            wait_zero(1);
-            if (!ready) {
-                __syncthreads();
-                load_band_head(frame, idx);
-            }
-            const uint32_t n_all = aux;                        // records of this band, in its bucket or overflowed
+            // =============================== band item ===============================
+            const BevRecord* rec = reinterpret_cast<const BevRecord*>(it.ptr);
+            const uint32_t n_all = n_all_pre;                  // records of this band, in its bucket or overflowed
             const uint32_t n_rec = min(n_all, a.bucket_cap);   // ... of which in the bucket
             const bool overflowed = n_all > a.bucket_cap;
+            wait_zero();
 
-            if (!overflowed && n_rec <= (uint32_t)(kFusedRegRecords * kFusedThreads)) {
+            if (!overflowed && n_rec <= (uint32_t)(kFusedRegRecords * kFusedWorkers)) {
                 uint4 r[kFusedRegRecords];
 #pragma unroll
                 for (int j = 0; j < kFusedSpecRecords; ++j) r[j] = pre[j];
 #pragma unroll
                 for (int j = kFusedSpecRecords; j < kFusedRegRecords; ++j) {
-                    const uint32_t i = tid + j * kFusedThreads;
-                    if (i < n_rec) r[j] = ld_record(rec + i);
+                    const uint32_t k = tid + j * kFusedWorkers;
+                    if (k < n_rec) r[j] = ld_record(rec + k);
                 }
 #pragma unroll
                 for (int j = 0; j < kFusedRegRecords; ++j) {
-                    const uint32_t i = tid + j * kFusedThreads;
-                    if (i < n_rec) {
+                    const uint32_t k = tid + j * kFusedWorkers;
+                    if (k < n_rec) {
                         atomicMax(&zkey[r[j].w], orderable_u32(__uint_as_float(r[j].x), 0u));   // NaN z sorts last (key 0)
                         atomicAdd(&cnt[r[j].w], 1u);
                     }
                 }
-                __syncthreads();
+                worker_barrier();
                 // A record alone in its cell is the winner: it writes the cell's final values at once.  Cells with
                 // several records vote on the lowest index among their highest-z records.
                 uint32_t multi = 0;
 #pragma unroll
                 for (int j = 0; j < kFusedRegRecords; ++j) {
-                    const uint32_t i = tid + j * kFusedThreads;
-                    if (i < n_rec) {
+                    const uint32_t k = tid + j * kFusedWorkers;
+                    if (k < n_rec) {
                         const uint32_t cell = r[j].w;
                         const uint32_t c = cnt[cell];
                         if (c == 1u) {
@@ -399,8 +492,7 @@ bev_fused_kernel(const __grid_constant__ FusedArgs a) {
                         }
                     }
                 }
-                if (tid == 0) publish(t_next, cur ^ 1);
-                __syncthreads();
+                worker_barrier();
 #pragma unroll
                 for (int j = 0; j < kFusedRegRecords; ++j) {
                     if ((multi >> j) & 1u) {
@@ -415,44 +507,17 @@ bev_fused_kernel(const __grid_constant__ FusedArgs a) {
                 }
             } else {
                 // crowded band: records streamed from L2 once per phase (bucket, and the frame's overflow list if needed)
-                const BevRecord* ovf = a.buckets + (size_t)slot * a.slot_recs + (size_t)nb * a.bucket_cap;
-                const uint32_t n_ovf = overflowed ? ld_cg_u32(ctl(kCtlOvf, slot)) : 0u;
-                if (tid == 0) publish(t_next, cur ^ 1);
-                band_stream_reduce<MUL_HEIGHT>(zkey, inv, cnt, inten, lut, rec, n_rec, ovf, n_ovf, (uint32_t)idx, a.g.max_h);
+                const BevRecord* ovf = a.buckets + (size_t)it.slot * a.slot_recs + (size_t)nb * a.bucket_cap;
+                const uint32_t n_ovf = overflowed ? ld_cg_u32(reinterpret_cast<const uint32_t*>(it.out)) : 0u;
+                worker_barrier();   // nobody is still in the previous item's copy-out / phase 3 (which use `inv`) — cheap on this rare path
+                band_stream_reduce<MUL_HEIGHT, kFusedWorkers>(zkey, inv, cnt, inten, lut, rec, n_rec, ovf, n_ovf, (uint32_t)it.idx, a.g.max_h);
             }
-            fence_proxy_async_smem();   // this thread's st.shared / atom.shared -> visible to the async proxy (TMA) ...
-            __syncthreads();            // ... and ordered before the bulk stores thread 0 issues below
-            prefetch_item(cur ^ 1);     // lands during the drain
-            if (tid == 0) {
-                *reinterpret_cast<volatile uint32_t*>(cursor_of(frame, idx)) = 0;   // cursor ready for the slot's next frame
-                // the last band of the frame to get here (all others have read the overflow counter already) resets it
-                if (atomicAdd(ctl(kCtlBandsPre, slot), 1u) + 1u == (use + 1u) * (uint32_t)nb)
-                    *reinterpret_cast<volatile uint32_t*>(ctl(kCtlOvf, slot)) = 0;
-                __threadfence();
-                atomicAdd(ctl(kCtlBandsDone, slot), 1u);
-                // the three shared arrays ARE the band's planes (empty cells kept their zero fill; channel 0
-                // intensity, 1 height, 2 density, kitti_bev_utils.py:50-53)
-                const size_t cells = (size_t)a.g.H * a.g.W;
-                const size_t cell0 = (size_t)idx * cpb;
-                const uint32_t bytes = (uint32_t)(min((size_t)cpb, cells - cell0) * sizeof(float));
-                float* const o = a.out + (size_t)frame * 3 * cells + cell0;
-                const unsigned long long pol = l2_evict_first_policy();
-                bulk_store_s2g_hint(o, inten, bytes, pol);
-                bulk_store_s2g_hint(o + cells, zkey, bytes, pol);
-                bulk_store_s2g_hint(o + 2 * cells, cnt, bytes, pol);
-                bulk_commit_group();
-                bulk_wait_group_read0();    // the planes have left shared memory ...
-                mbar_expect_tx(&zero_bar[0], 3u * (uint32_t)cpb * 4u);
-                bulk_load_g2s(inten, a.zeros, 3u * (uint32_t)cpb * 4u, &zero_bar[0]);   // ... and are zero-filled for the next band item
-            }
-            st |= 2u;
+            fence_proxy_async_smem();   // this thread's st.shared / atom.shared -> visible to the async proxy (TMA)
+            prefetch_next(i);           // lands during the drain
+            mbar_arrive(&tail_bar[buf]);
+            st |= 2u;                   // the service thread zero-fills the planes after the drain
         }
-        st ^= 1u;
     }
-    if (tid == 0) bulk_wait_group0();   // all plane stores performed before the CTA retires
-    // zero-fills still in flight target this CTA's shared memory: wait for them before it is released
-    wait_zero(0);
-    wait_zero(1);
     if (!RANGE_SAFE && a.status) {
         n_oob_total = __reduce_add_sync(0xFFFFFFFFu, n_oob_total);
         if ((tid & 31) == 0 && n_oob_total) atomicAdd(a.status, n_oob_total);
@@ -476,8 +541,8 @@ int fused_launch(const float* pts, const int64_t* offsets, int B, int64_t max_po
                  const BandPlan& plan, const float* lut, float* out, uint32_t* status, unsigned char* ws_base,
                  uint32_t* cursors, BevRecord* buckets, size_t slot_recs, uint32_t bucket_cap, int ring_avail,
                  cudaStream_t stream) {
-    static const int ring_want = fused_env("SFA_BEV_FUSED_RING", 8, 2, kFusedMaxRing);
-    static const int lag_want = fused_env("SFA_BEV_FUSED_LAG", 4, 1, kFusedMaxRing - 1);
+    static const int ring_want = fused_env("SFA_BEV_FUSED_RING", 16, 2, kFusedMaxRing);
+    static const int lag_want = fused_env("SFA_BEV_FUSED_LAG", 10, 1, kFusedMaxRing - 1);
     FusedArgs a;
     a.pts = reinterpret_cast<const float4*>(pts);
     a.offsets = offsets;

@@ -119,7 +119,23 @@ struct Lane {
 
 }  // namespace
 
+// Makes pl->device current for the duration of a pipeline call and puts the caller's device back afterwards (a process
+// that did cudaSetDevice(rank) must not find itself on another GPU after calling into the library).
+struct DeviceScope {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceScope(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+    }
+    ~DeviceScope() {
+        int now = -1;
+        if (prev >= 0 && cudaGetDevice(&now) == cudaSuccess && now != prev) cudaSetDevice(prev);
+    }
+};
+
 struct SfaPipeline {
+    std::mutex mutex;   // calls on one pipeline serialise (its lanes' staging buffers are shared state)
     int device = 0;
     int max_frames = 0, chunk = 0;
     int64_t max_points = 0;
@@ -130,9 +146,22 @@ struct SfaPipeline {
     Lane lanes[kLanes];
 };
 
+// Waits (blocking, not spinning: the events are created with cudaEventBlockingSync) until every lane has finished what
+// was enqueued on it; returns the first CUDA error.  Also the error path's drain: no copy into a caller's buffer is
+// left in flight when a pipeline call returns.
+static cudaError_t drain_lanes(SfaPipeline* pl) {
+    cudaError_t first = cudaSuccess;
+    for (Lane& l : pl->lanes) {
+        cudaError_t e = cudaEventRecord(l.done, l.stream);
+        if (e == cudaSuccess) e = cudaEventSynchronize(l.done);
+        if (e != cudaSuccess && first == cudaSuccess) first = e;
+    }
+    return first;
+}
+
 static void pipeline_free(SfaPipeline* pl) {
     if (!pl) return;
-    cudaSetDevice(pl->device);
+    DeviceScope dev(pl->device);
     for (Lane& l : pl->lanes) {
         if (l.stream) cudaStreamSynchronize(l.stream);
         cudaFree(l.d_pts); cudaFree(l.d_offsets); cudaFreeHost(l.h_offsets); cudaFree(l.d_out);
@@ -166,7 +195,8 @@ extern "C" SfaPipeline* sfa_pipeline_create(int32_t device, int32_t max_frames, 
     auto chk = [&](cudaError_t err, const char* what) {
         if (ok && err != cudaSuccess) { cuda_fail(err, what); ok = false; }
     };
-    chk(cudaSetDevice(device), "cudaSetDevice");
+    DeviceScope dev(device);
+    chk(dev.err, "cudaSetDevice");
     chk(cudaMalloc(&pl->d_lut, 64 * sizeof(float)), "cudaMalloc lut");
     chk(cudaMalloc(&pl->d_status, 2 * sizeof(uint32_t)), "cudaMalloc status");
     if (ok) chk(cudaMemcpy(pl->d_lut, density_lut_host, 64 * sizeof(float), cudaMemcpyHostToDevice), "copy lut");
@@ -176,7 +206,7 @@ extern "C" SfaPipeline* sfa_pipeline_create(int32_t device, int32_t max_frames, 
     for (Lane& l : pl->lanes) {
         if (!ok) break;
         chk(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking), "stream");
-        chk(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming), "event");
+        chk(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming | cudaEventBlockingSync), "event");
         size_t npts = (size_t)pl->chunk * (size_t)(max_points_per_frame > 0 ? max_points_per_frame : 1);
         chk(cudaMalloc(&l.d_pts, npts * 16), "cudaMalloc pts");
         chk(cudaMalloc(&l.d_offsets, (pl->chunk + 1) * sizeof(int64_t)), "cudaMalloc offsets");
@@ -207,18 +237,22 @@ extern "C" int sfa_pipeline_bev_host(SfaPipeline* pl, const float* pts_host, con
                                      float* out_host, uint32_t* status_host) {
     SFA_REQUIRE(pl && offsets_host && (out_host || B == 0), "NULL pointer argument");
     SFA_REQUIRE(B >= 0, "B must be >= 0");
-    SFA_CUDA_TRY(cudaSetDevice(pl->device));
+    std::lock_guard<std::mutex> lock(pl->mutex);
+    DeviceScope dev(pl->device);
+    SFA_CUDA_TRY(dev.err);
     const size_t cells = (size_t)pl->params.height * pl->params.width;
     for (int f = 0; f < B; ++f) {
         int64_t n = offsets_host[f + 1] - offsets_host[f];
         SFA_REQUIRE(n >= 0 && n <= pl->max_points, "sweep %d has %lld points; pipeline was created for <= %lld", f,
                     (long long)n, (long long)pl->max_points);
     }
+    int rc = SFA_OK;
+    auto cu = [&](cudaError_t e, const char* what) { if (rc == SFA_OK && e != cudaSuccess) rc = cuda_fail(e, what); return rc == SFA_OK; };
     int lane_i = 0;
-    for (int f0 = 0; f0 < B; f0 += pl->chunk, lane_i = (lane_i + 1) % kLanes) {
+    for (int f0 = 0; f0 < B && rc == SFA_OK; f0 += pl->chunk, lane_i = (lane_i + 1) % kLanes) {
         Lane& l = pl->lanes[lane_i];
         const int nf = B - f0 < pl->chunk ? B - f0 : pl->chunk;
-        SFA_CUDA_TRY(cudaEventSynchronize(l.done));  // pinned offsets of this lane are free again
+        if (!cu(cudaEventSynchronize(l.done), "lane wait")) break;   // pinned offsets of this lane are free again
         int64_t base = offsets_host[f0], mx = 0;
         for (int j = 0; j <= nf; ++j) l.h_offsets[j] = offsets_host[f0 + j] - base;
         for (int j = 0; j < nf; ++j) {
@@ -226,17 +260,18 @@ extern "C" int sfa_pipeline_bev_host(SfaPipeline* pl, const float* pts_host, con
             if (n > mx) mx = n;
         }
         const int64_t npts = l.h_offsets[nf];
-        SFA_CUDA_TRY(cudaMemcpyAsync(l.d_offsets, l.h_offsets, (nf + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, l.stream));
-        if (npts)
-            SFA_CUDA_TRY(cudaMemcpyAsync(l.d_pts, pts_host + base * 4, (size_t)npts * 16, cudaMemcpyHostToDevice, l.stream));
-        if (int rc = sfa_bev_rasterize(l.d_pts, l.d_offsets, nf, mx, &pl->params, pl->d_lut, l.d_out, pl->d_status,
-                                       l.d_ws, l.ws_bytes, l.stream))
-            return rc;
-        SFA_CUDA_TRY(cudaMemcpyAsync(out_host + (size_t)f0 * 3 * cells, l.d_out, (size_t)nf * 3 * cells * sizeof(float),
-                                     cudaMemcpyDeviceToHost, l.stream));
-        SFA_CUDA_TRY(cudaEventRecord(l.done, l.stream));
+        if (!cu(cudaMemcpyAsync(l.d_offsets, l.h_offsets, (nf + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, l.stream), "offsets H2D")) break;
+        if (npts && !cu(cudaMemcpyAsync(l.d_pts, pts_host + base * 4, (size_t)npts * 16, cudaMemcpyHostToDevice, l.stream), "sweeps H2D")) break;
+        rc = sfa_bev_rasterize(l.d_pts, l.d_offsets, nf, mx, &pl->params, pl->d_lut, l.d_out, pl->d_status, l.d_ws, l.ws_bytes, l.stream);
+        if (rc != SFA_OK) break;
+        if (!cu(cudaMemcpyAsync(out_host + (size_t)f0 * 3 * cells, l.d_out, (size_t)nf * 3 * cells * sizeof(float),
+                                cudaMemcpyDeviceToHost, l.stream), "maps D2H")) break;
+        cu(cudaEventRecord(l.done, l.stream), "lane record");
     }
-    for (Lane& l : pl->lanes) SFA_CUDA_TRY(cudaStreamSynchronize(l.stream));
+    // success or not, nothing stays in flight towards the caller's buffers
+    const cudaError_t drained = drain_lanes(pl);
+    if (rc == SFA_OK && drained != cudaSuccess) rc = cuda_fail(drained, "drain");
+    if (rc != SFA_OK) return rc;
     if (status_host) {
         SFA_CUDA_TRY(cudaMemcpy(status_host, pl->d_status, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
         SFA_CUDA_TRY(cudaMemset(pl->d_status, 0, 2 * sizeof(uint32_t)));
@@ -248,11 +283,15 @@ extern "C" int sfa_pipeline_decode_host(SfaPipeline* pl, const float* hm, const 
                                         const float* z_coor, const float* dim, int32_t B, float* det_host) {
     SFA_REQUIRE(pl && (B == 0 || (hm && direction && z_coor && dim && det_host)), "NULL pointer argument");
     SFA_REQUIRE(pl->C > 0, "pipeline was created without a decode stage");
-    SFA_CUDA_TRY(cudaSetDevice(pl->device));
+    std::lock_guard<std::mutex> lock(pl->mutex);
+    DeviceScope dev(pl->device);
+    SFA_CUDA_TRY(dev.err);
     const size_t hw = (size_t)pl->h * pl->w;
     const int C = pl->C, K = pl->K;
+    int rc = SFA_OK;
+    auto cu = [&](cudaError_t e, const char* what) { if (rc == SFA_OK && e != cudaSuccess) rc = cuda_fail(e, what); return rc == SFA_OK; };
     int lane_i = 0;
-    for (int f0 = 0; f0 < B; f0 += pl->chunk, lane_i = (lane_i + 1) % kLanes) {
+    for (int f0 = 0; f0 < B && rc == SFA_OK; f0 += pl->chunk, lane_i = (lane_i + 1) % kLanes) {
         Lane& l = pl->lanes[lane_i];
         const int nf = B - f0 < pl->chunk ? B - f0 : pl->chunk;
         float* d_hm = l.d_heads;
@@ -260,22 +299,20 @@ extern "C" int sfa_pipeline_decode_host(SfaPipeline* pl, const float* hm, const 
         float* d_dir = d_off + (size_t)pl->chunk * 2 * hw;
         float* d_z = d_dir + (size_t)pl->chunk * 2 * hw;
         float* d_dim = d_z + (size_t)pl->chunk * 1 * hw;
-        auto up = [&](float* dst, const float* src, int ch) -> cudaError_t {
-            return cudaMemcpyAsync(dst, src + (size_t)f0 * ch * hw, (size_t)nf * ch * hw * sizeof(float),
-                                   cudaMemcpyHostToDevice, l.stream);
+        auto up = [&](float* dst, const float* src, int ch) -> bool {
+            return cu(cudaMemcpyAsync(dst, src + (size_t)f0 * ch * hw, (size_t)nf * ch * hw * sizeof(float),
+                                      cudaMemcpyHostToDevice, l.stream), "heads H2D");
         };
-        SFA_CUDA_TRY(up(d_hm, hm, C));
-        if (cen_offset) SFA_CUDA_TRY(up(d_off, cen_offset, 2));
-        SFA_CUDA_TRY(up(d_dir, direction, 2));
-        SFA_CUDA_TRY(up(d_z, z_coor, 1));
-        SFA_CUDA_TRY(up(d_dim, dim, 3));
-        if (int rc = sfa_decode(d_hm, cen_offset ? d_off : nullptr, d_dir, d_z, d_dim, nf, C, pl->h, pl->w, K, l.d_det,
-                                nullptr, 0, l.d_dec_ws, l.dec_ws_bytes, l.stream))
-            return rc;
-        SFA_CUDA_TRY(cudaMemcpyAsync(det_host + (size_t)f0 * K * 10, l.d_det, (size_t)nf * K * 10 * sizeof(float),
-                                     cudaMemcpyDeviceToHost, l.stream));
-        SFA_CUDA_TRY(cudaEventRecord(l.done, l.stream));
+        if (!up(d_hm, hm, C)) break;
+        if (cen_offset && !up(d_off, cen_offset, 2)) break;
+        if (!up(d_dir, direction, 2) || !up(d_z, z_coor, 1) || !up(d_dim, dim, 3)) break;
+        rc = sfa_decode(d_hm, cen_offset ? d_off : nullptr, d_dir, d_z, d_dim, nf, C, pl->h, pl->w, K, l.d_det,
+                        nullptr, 0, l.d_dec_ws, l.dec_ws_bytes, l.stream);
+        if (rc != SFA_OK) break;
+        cu(cudaMemcpyAsync(det_host + (size_t)f0 * K * 10, l.d_det, (size_t)nf * K * 10 * sizeof(float),
+                           cudaMemcpyDeviceToHost, l.stream), "detections D2H");
     }
-    for (Lane& l : pl->lanes) SFA_CUDA_TRY(cudaStreamSynchronize(l.stream));
-    return SFA_OK;
+    const cudaError_t drained = drain_lanes(pl);
+    if (rc == SFA_OK && drained != cudaSuccess) rc = cuda_fail(drained, "drain");
+    return rc;
 }

@@ -1,0 +1,11 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT"; mkdir -p gpurun_out
+python lidar*/build.py > /dev/null || exit 1
+timeout 600 python -m pytest tests/test_bev_gpu.py -x -q -m gpu -k "tiled" > gpurun_out/r2f_pytest.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/r2f_pytest.log
+for v in "lag4r8 SFA_BEV_FUSED_LAG=4 SFA_BEV_FUSED_RING=8" "lag6r10 SFA_BEV_FUSED_LAG=6 SFA_BEV_FUSED_RING=10" "lag8r12 SFA_BEV_FUSED_LAG=8 SFA_BEV_FUSED_RING=12" "lag10r16 SFA_BEV_FUSED_LAG=10 SFA_BEV_FUSED_RING=16" "lag14r20 SFA_BEV_FUSED_LAG=14 SFA_BEV_FUSED_RING=20" "lag20r28 SFA_BEV_FUSED_LAG=20 SFA_BEV_FUSED_RING=28"; do
+  set -- $v; name=$1; shift
+  echo "$name: $(env "$@" timeout 120 python tools/bev_run.py 30 1 2>&1 | tail -1)"
+done
+SFA_BEV_FUSED=1 timeout 300 python tools/bev_distributions.py > gpurun_out/r2f_dist.log 2>&1; grep "us per 64 frames  (" gpurun_out/r2f_dist.log
+ncu --set full --clock-control none --cache-control none --import-source on -k regex:bev_fused -s 4 -c 1 -f -o gpurun_out/r2f_fused python tools/bev_run.py 4 1 > gpurun_out/r2f_ncu.log 2>&1
+echo "ncu rc=$?"; tail -3 gpurun_out/r2f_ncu.log
