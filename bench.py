@@ -803,9 +803,9 @@ def main():
     ap.add_argument("--config", default="headline", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--sets", type=int, default=4)
-    ap.add_argument("--pipelines", type=int, default=1,
+    ap.add_argument("--pipelines", type=int, default=2,
                     help="engines (own workspaces, outputs, streams) that take the steps in turn, so consecutive steps overlap")
-    ap.add_argument("--lanes", type=int, default=1, help="independent BEV streams the batch is split over")
+    ap.add_argument("--lanes", type=int, default=2, help="independent BEV streams the batch is split over")
     ap.add_argument("--decode-stream", action="store_true", help="decode on a stream of its own even with one BEV lane")
     ap.add_argument("--e2e-workers", type=int, default=2, help="host threads of the e2e leg, each with its own pipelines")
     ap.add_argument("--settle-s", type=float, default=0.5, help="seconds of untimed steps before the warm-up (clock ramp, sampler)")

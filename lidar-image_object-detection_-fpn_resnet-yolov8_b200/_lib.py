@@ -22,6 +22,12 @@ class SfaBevParams(ctypes.Structure):
 BEV_AUTO, BEV_TILED, BEV_GLOBAL_ATOMIC, BEV_TILED_TWO_KERNEL = 0, 1, 2, 3   # enum SfaBevAlgorithm
 
 
+class SfaBevExtras(ctypes.Structure):
+    """struct SfaBevExtras of include/sfa_b200.h (sweep-side extras of sfa_bev_rasterize_ex)."""
+    _fields_ = [("mats", c_void_p), ("n_mats", i32), ("scales", c_void_p), ("hflip", c_void_p),
+                ("second", ctypes.POINTER(SfaBevParams)), ("out_second", c_void_p)]
+
+
 class SfaBvParams(ctypes.Structure):
     """struct SfaBvParams of include/sfa_b200.h (makeBVFeature geometry)."""
     _fields_ = [("min_x", f32), ("max_x", f32), ("min_y", f32), ("max_y", f32), ("min_z", f32), ("max_z", f32),
@@ -52,6 +58,8 @@ PROTOTYPES = {
                                          ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(i32)]),
     "sfa_bev_rasterize": (ctypes.c_int, [c_void_p, c_void_p, i32, i64, ctypes.POINTER(SfaBevParams), c_void_p,
                                          c_void_p, c_void_p, c_void_p, sz, c_void_p]),
+    "sfa_bev_rasterize_ex": (ctypes.c_int, [c_void_p, c_void_p, i32, i64, ctypes.POINTER(SfaBevParams),
+                                            ctypes.POINTER(SfaBevExtras), c_void_p, c_void_p, c_void_p, c_void_p, sz, c_void_p]),
     "sfa_selftest_division": (ctypes.c_int, [f32, ctypes.c_uint32, ctypes.c_uint64, c_void_p, c_void_p]),
     "sfa_filter_workspace_bytes": (sz, [i64]),
     "sfa_filter_lidar": (ctypes.c_int, [c_void_p, i64, ctypes.POINTER(SfaBevParams), c_void_p, c_void_p, c_void_p,

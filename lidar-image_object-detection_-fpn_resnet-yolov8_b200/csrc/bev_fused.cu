@@ -48,7 +48,7 @@ constexpr int kCtlBandsDone = 1 + kFusedMaxRing;
 constexpr int kCtlOvf = 1 + 2 * kFusedMaxRing;                 // two per ring slot (+ kFusedMaxRing for odd uses)
 constexpr int kCtlTimeouts = 1 + 4 * kFusedMaxRing;
 constexpr size_t kFusedCtlBytes = (size_t)(2 + 4 * kFusedMaxRing) * kCtlLine * sizeof(uint32_t);
-constexpr size_t kFusedZerosOffset = 24576;
+constexpr size_t kFusedZerosOffset = kZerosOffset;
 static_assert(kFusedWorkers >= kFusedBands && kFusedWorkers % 32 == 0, "one scan thread per band");
 static_assert(kFusedCtlOffset + kFusedCtlBytes <= kFusedZerosOffset, "control block overlaps the zero block");
 static_assert(kFusedZerosOffset + 3 * (size_t)kMaxCellsPerBand * sizeof(uint32_t) <= kHeaderBytes, "zero block does not fit the header");
@@ -84,44 +84,6 @@ __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {
     asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_addr_u32(bar)), "r"(parity), "r"(200u)
-        : "memory");
-}
-// the service thread's wait: the hardware may suspend the thread for up to ~1 us per probe instead of spinning
-__device__ __forceinline__ void mbar_wait_relaxed(unsigned long long* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAITR_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-        "@p bra DONER_%=;\n"
-        "bra WAITR_%=;\n"
-        "DONER_%=:\n"
-        "}\n" ::"r"(smem_addr_u32(bar)), "r"(parity), "r"(1000u)
-        : "memory");
-}
-// global -> shared::cta bulk copy, completion (bytes) on an mbarrier of this CTA
-__device__ __forceinline__ void bulk_load_g2s(void* sdst, const void* gsrc, uint32_t bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr_u32(sdst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_addr_u32(bar))
-                 : "memory");
-}
-
 // Ticket t = (step s = t / P, k = t % P), P = max(tiles per frame, bands per frame): the bin tile k of frame s (if any)
 // and then the band k of frame s - LAG (if any).  A CTA therefore alternates bin tile / band item: the TMA drain and
 // zero-fill of a band's planes hide behind the next bin tile.
@@ -150,23 +112,6 @@ struct __align__(16) FusedItem {   // what the service thread publishes for the 
 };
 
 __device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kFusedWorkers) : "memory"); }
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_test(unsigned long long* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_addr_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-
 // The kernel.  Threads 0 .. kFusedWorkers-1 are WORKERS (all the arithmetic); lane 0 of the last warp is the SERVICE
 // thread: it claims tickets, waits for an item's dependencies, publishes the item (pointers, counts) one item ahead of
 // the workers, and after the workers are done with an item performs its tail — release fence + completion signal,

@@ -41,8 +41,14 @@ constexpr int kCandWarps = kCandThreads / 32;
 constexpr int kCandRows = 16;              // rows of a slab
 constexpr int kCapClasses = 8;             // plateau cap: classes a column group may span ...
 constexpr int kCapWords = 16;              // ... and 32-bit words per map row (w <= 512)
-constexpr int kSelThreads = 1024;
-constexpr int kSelSmemItems = 12288;       // candidate words selected from shared memory (96 KB)
+#ifndef SFA_SEL_THREADS
+#define SFA_SEL_THREADS 1024
+#endif
+#ifndef SFA_SEL_SMEM_ITEMS
+#define SFA_SEL_SMEM_ITEMS 12288
+#endif
+constexpr int kSelThreads = SFA_SEL_THREADS;
+constexpr int kSelSmemItems = SFA_SEL_SMEM_ITEMS;   // candidate words selected from shared memory (96 KB)
 constexpr int kSelUnroll = 4;              // list entries a select thread loads before it processes them
 constexpr int kSelTieWindow = 8192;        // tie-break shortcut: tied cells with a linear index below this
 constexpr int kMaxK = 128;
@@ -386,7 +392,9 @@ __device__ void block_radix_select(WordFn word, int n, unsigned need, SelectShar
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const bool a = active[u] && ((k[u] ^ prefix) & himask) == 0;
-                if (PEEL) hist_add(sh.hist, a, (k[u] >> shift) & 255u, lane);
+                // pass 0 bins by sign + 7 exponent bits: scores of one map share two or three of them, and same-address
+                // shared atomics serialise — aggregate per warp there whatever the list looks like
+                if (PEEL || pass == 0) hist_add(sh.hist, a, (k[u] >> shift) & 255u, lane);
                 else if (a) atomicAdd(&sh.hist[(k[u] >> shift) & 255u], 1u);
             }
         }

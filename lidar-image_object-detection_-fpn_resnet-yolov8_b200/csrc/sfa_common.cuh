@@ -97,6 +97,63 @@ __device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async
 // ... have completed entirely
 __device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ---- mbarriers (shared::cta) and global -> shared bulk copies completing on them ----------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_addr_u32(bar)), "r"(parity), "r"(200u)
+        : "memory");
+}
+// the service thread's wait: the hardware may suspend the thread for up to ~1 us per probe instead of spinning
+__device__ __forceinline__ void mbar_wait_relaxed(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITR_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONER_%=;\n"
+        "bra WAITR_%=;\n"
+        "DONER_%=:\n"
+        "}\n" ::"r"(smem_addr_u32(bar)), "r"(parity), "r"(1000u)
+        : "memory");
+}
+// global -> shared::cta bulk copy, completion (bytes) on an mbarrier of this CTA
+__device__ __forceinline__ void bulk_load_g2s(void* sdst, const void* gsrc, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr_u32(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_addr_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_addr_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+
 // ---- order-preserving float -> uint32 maps -------------------------------------------------------
 // Total order of the float VALUES (-0.0 == +0.0); `nan_key` is where NaN goes.
 __device__ __forceinline__ uint32_t orderable_u32(float f, uint32_t nan_key) {

@@ -5,26 +5,36 @@ The drawing helpers of that file (get_corners, drawRotatedBox; cv2) are out of s
 
 Geometry comes from `cnf` (module global, like the reference); assign `cnf = other_module` to
 rasterise another range (the reference is monkey-patched the same way for Argoverse ranges)."""
+import threading
+
 import numpy as np
 
 from ..config import kitti_config as cnf  # noqa: F401  (module global on purpose, see above)
 from .. import geometry as _geometry
 
 _pipelines = {}
+_pipelines_lock = threading.Lock()
 
 
 def _pipeline(boundary, apply_filter, n_points):
-    """One cached HostPipeline per (geometry, filter) — grown when a larger sweep arrives."""
+    """One cached HostPipeline per (CUDA device, geometry, filter) — the calling thread's CURRENT device, like any
+    torch op — grown when a larger sweep arrives.  The cache is guarded by a lock; calls on one pipeline serialise
+    inside the library (SfaPipeline holds a mutex)."""
+    import torch
     from ..fast import HostPipeline
     geom = _geometry.BevGeometry(boundary, cnf, apply_filter=apply_filter)
-    key = geom.key()
-    pl = _pipelines.get(key)
-    if pl is None or pl.max_points < n_points:
-        if pl is not None:
-            pl.close()
-        cap = max(131072, 1 << int(np.ceil(np.log2(max(n_points, 1)))))
-        pl = HostPipeline(geom, max_frames=1, max_points=cap, C=0, h=1, w=1, K=1)
-        _pipelines[key] = pl
+    if not torch.cuda.is_available():
+        raise RuntimeError("libsfa_b200 needs a CUDA device (there is no CPU fallback)")
+    device = torch.cuda.current_device()
+    key = (device,) + tuple(geom.key())
+    with _pipelines_lock:
+        pl = _pipelines.get(key)
+        if pl is None or pl.max_points < n_points:
+            if pl is not None:
+                pl.close()
+            cap = max(131072, 1 << int(np.ceil(np.log2(max(n_points, 1)))))
+            pl = HostPipeline(geom, max_frames=1, max_points=cap, C=0, h=1, w=1, K=1, device=device)
+            _pipelines[key] = pl
     return pl
 
 

@@ -6,9 +6,10 @@ float64; the batched device form is fast.project_boxes_dense.
 Also the sweep side of the training augmentation: `point_transform` (:242-285), `Random_Rotation`
 (:338-354) and `Random_Scaling` (:357-371) with the reference's np.random call sequence; the rigid
 transform runs in `sfa_transform_points` (float64 FMA chains like numpy's dgemm, bit-identical).  The
-LABEL side of those classes (`box_transform`: <= 50 boxes through corner conversions) is host code
-outside the hot path: pass the reference's own `box_transform` as `box_transform=` to keep labels in
-step, or leave it None when only the sweep is augmented (inference-time test augmentation)."""
+LABEL side of Random_Rotation (`box_transform`: <= 50 boxes through corner conversions, transformation.py:288-305)
+is host code outside the hot path and is not re-implemented here: pass the reference's own `box_transform`
+as `box_transform=`.  Without it Random_Rotation REFUSES to rotate a sweep that comes with labels (it raises
+instead of silently leaving the targets unrotated); a sweep without labels (inference-time augmentation) needs none."""
 import numpy as np
 import torch
 
@@ -95,6 +96,10 @@ class Random_Rotation(object):
     def __call__(self, lidar, labels):
         if np.random.random() <= self.p:
             angle = np.random.uniform(-self.limit_angle, self.limit_angle)
+            if self.box_transform is None and labels is not None and np.size(labels) > 0:
+                # the reference always rotates the labels with the sweep (transformation.py:351)
+                raise ValueError("Random_Rotation got labels but no box_transform: pass the reference's "
+                                 "data_process.transformation.box_transform (the sweep would be rotated, the labels not)")
             dev = _device()
             pts = torch.from_numpy(lidar).to(dev)          # float32 [N, >= 3], transformed in place like the reference
             mats = torch.from_numpy(_matrices(0, 0, 0, rz=angle)).to(dev)

@@ -48,8 +48,10 @@ class BevRasterizer:
             raise _lib.SfaError(-1, _lib.last_error() or "bad geometry")
         if share_with is not None:
             if (share_with._ws_bytes < nbytes or share_with.device != self.device or
-                    not np.array_equal(share_with.geom.lut32, geom.lut32)):
-                raise ValueError("share_with must be a rasterizer on the same device with a workspace at least as large")
+                    not np.array_equal(share_with.geom.lut32, geom.lut32) or share_with.geom.algorithm != geom.algorithm or
+                    (share_with.geom.height, share_with.geom.width) != (geom.height, geom.width)):
+                raise ValueError("share_with must be a rasterizer on the same device with the same map size, algorithm and "
+                                 "density table and a workspace at least as large")
             self.workspace, self._ws_ptr, self._ws_bytes = share_with.workspace, share_with._ws_ptr, share_with._ws_bytes
             self.lut, self.status = share_with.lut, share_with.status
             return
@@ -63,13 +65,22 @@ class BevRasterizer:
             _lib.check(self.lib.sfa_bev_workspace_init(ctypes.c_void_p(self._ws_ptr), self._ws_bytes,
                                                        _stream_ptr(self.device)))
 
-    def __call__(self, points, offsets, max_points, out=None):
+    def __call__(self, points, offsets, max_points, out=None, mats=None, scales=None, hflip=None, second=None, out_second=None):
         """points [total,4] f32 cuda, offsets [B+1] i64 cuda (or None for a uniform batch of sweeps with
         exactly max_points points each), max_points: python int upper bound on the points of any sweep.
-        Returns out [B,3,H,W] f32 (channel 0 intensity, 1 height, 2 density)."""
+        Returns out [B,3,H,W] f32 (channel 0 intensity, 1 height, 2 density).
+        Sweep-side extras, applied to each point while it is in registers (sfa_bev_rasterize_ex; one read of the sweep):
+          mats   CUDA float64 [B, m, 4, 4], scales CUDA float32 [B]: the training augmentation in front of the filter
+                 (Random_Rotation / Random_Scaling, data_process/transformation.py:349-352, :366-368)
+          hflip  CUDA uint8 / bool [B]: mirror that frame's map left-right (torch.flip(bev_map, [-1]), kitti_dataset.py:93-97)
+          second a BevGeometry differing in its boundary only, rasterised from the same read into out_second
+                 (front + back maps, demo_dataset.py:70-88); the call then returns (out, out_second)."""
         _require_cuda(points, "points")
         if points.dtype != torch.float32 or not points.is_contiguous():
             raise TypeError("points must be contiguous float32")
+        if points.device != self.device or (offsets is not None and offsets.device != self.device) or \
+                (out is not None and out.device != self.device):
+            raise ValueError("points / offsets / out must live on the rasteriser's device %s" % self.device)
         if offsets is None:      # uniform batch: every sweep holds exactly max_points points
             if int(max_points) <= 0 or points.numel() % (4 * int(max_points)):
                 raise ValueError("a uniform batch needs total_points to be a multiple of max_points")
@@ -87,10 +98,50 @@ class BevRasterizer:
             out = torch.empty((B, 3, g.height, g.width), dtype=torch.float32, device=self.device)
         elif out.shape != (B, 3, g.height, g.width) or out.dtype != torch.float32 or not out.is_contiguous():
             raise ValueError("out must be contiguous float32 [B,3,H,W]")
-        _lib.check(self.lib.sfa_bev_rasterize(_ptr(points), _ptr(offsets), B, int(max_points),
-                                              ctypes.byref(g.params), _ptr(self.lut), _ptr(out), _ptr(self.status),
-                                              ctypes.c_void_p(self._ws_ptr), self._ws_bytes, _stream_ptr(self.device)))
-        return out
+        if mats is None and scales is None and hflip is None and second is None:
+            with torch.cuda.device(self.device):   # (any B: the frames stream through the workspace's ring)
+                _lib.check(self.lib.sfa_bev_rasterize(_ptr(points), _ptr(offsets), B, int(max_points),
+                                                      ctypes.byref(g.params), _ptr(self.lut), _ptr(out), _ptr(self.status),
+                                                      ctypes.c_void_p(self._ws_ptr), self._ws_bytes, _stream_ptr(self.device)))
+            return out
+        ex = _lib.SfaBevExtras()
+        keep = []   # tensors the struct points to
+        if mats is not None:
+            if mats.dim() == 3:
+                mats = mats[None]
+            if (not mats.is_cuda or mats.device != self.device or mats.dtype != torch.float64 or mats.dim() != 4 or
+                    mats.shape[0] != B or tuple(mats.shape[2:]) != (4, 4) or mats.shape[1] > 4):
+                raise ValueError("mats must be a CUDA float64 [B, m <= 4, 4, 4] tensor on %s" % self.device)
+            mats = mats.contiguous()
+            keep.append(mats)
+            ex.mats, ex.n_mats = mats.data_ptr(), int(mats.shape[1])
+        if scales is not None:
+            if not scales.is_cuda or scales.device != self.device or scales.dtype != torch.float32 or scales.numel() != B:
+                raise ValueError("scales must be a CUDA float32 [B] tensor on %s" % self.device)
+            scales = scales.contiguous()
+            keep.append(scales)
+            ex.scales = scales.data_ptr()
+        if hflip is not None:
+            if not hflip.is_cuda or hflip.device != self.device or hflip.numel() != B:
+                raise ValueError("hflip must be a CUDA [B] tensor on %s" % self.device)
+            hflip = hflip.to(torch.uint8).contiguous()
+            keep.append(hflip)
+            ex.hflip = hflip.data_ptr()
+        if second is not None:
+            if out_second is None:
+                out_second = torch.empty((B, 3, g.height, g.width), dtype=torch.float32, device=self.device)
+            elif (out_second.shape != (B, 3, g.height, g.width) or out_second.dtype != torch.float32 or
+                  not out_second.is_contiguous() or out_second.device != self.device):
+                raise ValueError("out_second must be contiguous float32 [B,3,H,W] on %s" % self.device)
+            if self.max_batch < 2:
+                raise ValueError("two maps per sweep need a workspace sized for max_batch >= 2")
+            ex.second = ctypes.pointer(second.params)
+            ex.out_second = out_second.data_ptr()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sfa_bev_rasterize_ex(_ptr(points), _ptr(offsets), B, int(max_points), ctypes.byref(g.params),
+                                                     ctypes.byref(ex), _ptr(self.lut), _ptr(out), _ptr(self.status),
+                                                     ctypes.c_void_p(self._ws_ptr), self._ws_bytes, _stream_ptr(self.device)))
+        return out if second is None else (out, out_second)
 
     def rasterize_uniform(self, points, out=None):
         """points [B,N,4]: every sweep has N points (no offsets array, no dependent load in the kernels)."""
@@ -107,23 +158,21 @@ class BevRasterizer:
 
 
 class FrontBackRasterizer:
-    """The front + back pair of the 2-sides demo (data_process/demo_dataset.py:70-88): the same sweeps
-    filtered and rasterised once with cnf.boundary and once with cnf.boundary_back (negative x rows wrap
-    like numpy's negative indices).  Two passes of the kernels over the device-resident sweeps on one
-    stream, sharing one workspace; returns (front [B,3,H,W], back [B,3,H,W])."""
+    """The front + back pair of the 2-sides demo (data_process/demo_dataset.py:70-88): the same sweeps filtered and
+    rasterised with cnf.boundary and with cnf.boundary_back (negative x rows wrap like numpy's negative indices), from
+    ONE read of each sweep: every point is mapped with both geometries while it sits in registers and its records go
+    to the buckets of the front or the back map (sfa_bev_rasterize_ex).  Returns (front [B,3,H,W], back [B,3,H,W])."""
 
     def __init__(self, cnf=None, max_batch: int = 64, max_points: int = 131072, device=None):
         from .config import kitti_config
         from . import geometry
         cnf = kitti_config if cnf is None else cnf
-        self.front = BevRasterizer(geometry.from_config(cnf, cnf.boundary), max_batch, max_points, device)
-        self.back = BevRasterizer(geometry.from_config(cnf, cnf.boundary_back), max_batch, max_points, device,
-                                  share_with=self.front)
+        self.front = BevRasterizer(geometry.from_config(cnf, cnf.boundary), max(2, max_batch), max_points, device)
+        self.back_geom = geometry.from_config(cnf, cnf.boundary_back)
 
     def __call__(self, points, offsets, max_points, out=None):
         front_out, back_out = (None, None) if out is None else out
-        return (self.front(points, offsets, max_points, out=front_out),
-                self.back(points, offsets, max_points, out=back_out))
+        return self.front(points, offsets, max_points, out=front_out, second=self.back_geom, out_second=back_out)
 
 
 def filter_lidar_device(points, geom: BevGeometry):
@@ -361,6 +410,9 @@ class BvFeatureRasterizer:
             raise ValueError("max_points %d exceeds the %d the workspace was sized for" % (max_points, self.max_points))
         if out is None:
             out = torch.empty((B, 3, self.H, self.W), dtype=torch.float32, device=self.device)
+        elif (not out.is_cuda or out.device != self.device or out.dtype != torch.float32 or not out.is_contiguous() or
+              tuple(out.shape) != (B, 3, self.H, self.W)):
+            raise ValueError("out must be a contiguous float32 CUDA tensor [B,3,%d,%d] on %s" % (self.H, self.W, self.device))
         with torch.cuda.device(self.device):
             _lib.check(self.lib.sfa_bvfeature_rasterize(_ptr(points), _ptr(offsets), B, int(max_points),
                                                         ctypes.byref(self.params), _ptr(out), _ptr(self.ws),
@@ -429,14 +481,21 @@ class HostPipeline:
     overlapped H2D -> kernels -> D2H inside the library.  This is what the drop-in makeBEVMap /
     decode wrappers and bench.py's `e2e` leg call."""
 
-    def __init__(self, geom: BevGeometry, max_frames=64, max_points=131072, C=3, h=152, w=152, K=50, device=0):
+    def __init__(self, geom: BevGeometry, max_frames=64, max_points=131072, C=3, h=152, w=152, K=50, device=None):
+        """device: CUDA device index (default: the calling thread's current device, like every torch op)."""
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("HostPipeline needs a CUDA device (there is no CPU fallback)")
+        if device is None:
+            device = torch.cuda.current_device()
+        elif not isinstance(device, int):
+            device = torch.device(device).index
+            device = torch.cuda.current_device() if device is None else device
+        self.device = int(device)
         self.geom, self.max_frames, self.max_points = geom, int(max_frames), int(max_points)
         self.C, self.h, self.w, self.K = C, h, w, K
         lut = np.ascontiguousarray(geom.lut32)
-        self._h = self.lib.sfa_pipeline_create(int(device), self.max_frames, self.max_points, ctypes.byref(geom.params),
+        self._h = self.lib.sfa_pipeline_create(self.device, self.max_frames, self.max_points, ctypes.byref(geom.params),
                                                lut.ctypes.data_as(ctypes.c_void_p), C, h, w, K)
         if not self._h:
             raise _lib.SfaError(-3, _lib.last_error())
@@ -455,9 +514,13 @@ class HostPipeline:
         offs = _as_host(offsets, np.int64)
         B = offs.shape[0] - 1
         g = self.geom
+        if pts.ndim != 2 or pts.shape[1] != 4:
+            raise ValueError("points must be [total, 4] float32")
+        if B < 0 or (B > 0 and (offs[0] < 0 or np.any(np.diff(offs) < 0) or offs[-1] > pts.shape[0])):
+            raise ValueError("offsets must be non-decreasing, start at >= 0 and end within the %d points given" % pts.shape[0])
         if out is None:
             out = np.empty((B, 3, g.height, g.width), dtype=np.float32)
-        o = _as_host(out, np.float32)
+        o = _as_out(out, (B, 3, g.height, g.width), "out")
         status = np.zeros(2, dtype=np.uint32)
         _lib.check(self.lib.sfa_pipeline_bev_host(ctypes.c_void_p(self._h), pts.ctypes.data_as(ctypes.c_void_p),
                                                   offs.ctypes.data_as(ctypes.c_void_p), B,
@@ -472,13 +535,28 @@ class HostPipeline:
         B = hm_.shape[0]
         if hm_.shape[1:] != (self.C, self.h, self.w):
             raise ValueError("pipeline was created for heads %s, got %s" % ((self.C, self.h, self.w), hm_.shape[1:]))
+        for name, t, ch in (("cen_offset", off_, 2), ("direction", dir_, 2), ("z_coor", z_, 1), ("dim", dim_, 3)):
+            if t is not None and t.shape != (B, ch, self.h, self.w):
+                raise ValueError("%s must be [%d,%d,%d,%d], got %s" % (name, B, ch, self.h, self.w, t.shape))
         if out is None:
             out = np.empty((B, self.K, 10), dtype=np.float32)
-        o = _as_host(out, np.float32)
+        o = _as_out(out, (B, self.K, 10), "out")
         vp = lambda a: a.ctypes.data_as(ctypes.c_void_p) if a is not None else ctypes.c_void_p(0)
         _lib.check(self.lib.sfa_pipeline_decode_host(ctypes.c_void_p(self._h), vp(hm_), vp(off_), vp(dir_), vp(z_),
                                                      vp(dim_), B, vp(o)))
         return out
+
+
+def _as_out(a, shape, name):
+    """A caller-supplied output buffer is written IN PLACE by the C side: it must already be what the C side expects
+    (a silently made copy would swallow the results; a smaller buffer would be overrun)."""
+    if isinstance(a, torch.Tensor):
+        if a.is_cuda:
+            raise TypeError("%s must be a host tensor" % name)
+        a = a.detach().numpy()
+    if not isinstance(a, np.ndarray) or a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"] or tuple(a.shape) != tuple(shape):
+        raise ValueError("%s must be a C-contiguous float32 array of shape %s" % (name, tuple(shape)))
+    return a
 
 
 def _as_host(a, dtype):

@@ -11,6 +11,7 @@ host-buffer pipeline and come back as CPU tensors.  There is no CPU compute path
 Tie rule: among EQUAL scores torch.topk's order is implementation-defined; here it is lower class
 first, then lower y*w+x."""
 import ctypes
+import threading
 
 import numpy as np
 import torch
@@ -19,6 +20,7 @@ from .. import _lib
 from ..config import kitti_config as cnf
 
 _host_pipelines = {}
+_host_pipelines_lock = threading.Lock()
 
 
 def _stream(t):
@@ -92,13 +94,16 @@ def decode(hm_cen, cen_offset, direction, z_coor, dim, K=40):
     if not hm_cen.is_cuda:
         from ..fast import HostPipeline
         from .. import geometry as _geometry
-        key = (C, h, w, K)
-        pl = _host_pipelines.get(key)
-        if pl is None or pl.max_frames < B:
-            if pl is not None:
-                pl.close()
-            pl = HostPipeline(_geometry.from_config(cnf), max_frames=max(B, 8), max_points=0, C=C, h=h, w=w, K=K)
-            _host_pipelines[key] = pl
+        device = torch.cuda.current_device()   # CPU tensors: the calling thread's current device, like any torch op
+        key = (device, C, h, w, K)
+        with _host_pipelines_lock:
+            pl = _host_pipelines.get(key)
+            if pl is None or pl.max_frames < B:
+                if pl is not None:
+                    pl.close()
+                pl = HostPipeline(_geometry.from_config(cnf), max_frames=max(B, 8), max_points=0, C=C, h=h, w=w, K=K,
+                                  device=device)
+                _host_pipelines[key] = pl
         try:
             det = pl.decode(hm_cen, cen_offset, direction, z_coor, dim)
         except _lib.SfaError as e:

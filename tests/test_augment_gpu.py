@@ -42,7 +42,8 @@ def test_random_rotation_and_scaling_mirrors_follow_the_rng_stream(mods, fixture
     sweep, labels = z["sweep"], z["labels"]
     for k, seed in enumerate((1, 2, 3, 4)):
         np.random.seed(seed)
-        lidar, lab = tr.Random_Rotation(limit_angle=np.pi / 4, p=1.0)(sweep.copy(), labels.copy())
+        # the label side is the caller's (reference's) box_transform; an identity stands in for it here
+        lidar, lab = tr.Random_Rotation(limit_angle=np.pi / 4, p=1.0, box_transform=lambda b, *a, **kw: b)(sweep.copy(), labels.copy())
         assert np.array_equal(lidar.view(np.uint32), z["rot%d" % k].view(np.uint32))
         assert np.random.random() == float(z["rot%d_next" % k]) and np.array_equal(lab, labels)
         np.random.seed(seed)
@@ -52,6 +53,12 @@ def test_random_rotation_and_scaling_mirrors_follow_the_rng_stream(mods, fixture
     np.random.seed(7)
     lidar, _ = tr.Random_Rotation(p=0.0)(sweep.copy(), labels.copy())     # not drawn: untouched
     assert np.array_equal(lidar.view(np.uint32), sweep.view(np.uint32))
+    # labels without a box_transform: refuse (the reference always rotates the labels with the sweep, transformation.py:351)
+    with pytest.raises(ValueError):
+        tr.Random_Rotation(p=1.0)(sweep.copy(), labels.copy())
+    np.random.seed(7)
+    lidar, lab = tr.Random_Rotation(p=1.0)(sweep.copy(), np.zeros((0, 8), np.float32))    # no labels: fine
+    assert lab.shape == (0, 8) and not np.array_equal(lidar, sweep)
     called = []
     tr.Random_Rotation(p=1.0, box_transform=lambda b, *a, **k: called.append((a, k)) or b)(sweep.copy(), labels.copy())
     assert called and called[0][1]["coordinate"] == "lidar"

@@ -463,3 +463,60 @@ def test_front_and_back_pair_of_the_two_sides_demo(cuda_device):
         _assert_bit_exact(back[i].cpu().numpy(), O.make_bev_scatter(s, O.KITTI_BACK, True, np.float32), "back %d" % i)
     assert float(back[0, 2, 0].sum()) > 0 and float(front[0, 2, 0].sum()) > 0      # the x == 0 points, row 0 of both
     assert pair.front.out_of_map_points() == 0
+
+
+def test_bev_extras_augmentation_prologue_and_hflip(cuda_device):
+    """sfa_bev_rasterize_ex: Random_Rotation + Random_Scaling applied to the points inside the raster kernel (no augmented
+    sweep in HBM) and the horizontal flip as a mirrored column index.  Oracle: the reference's order of operations —
+    augment the sweep (data_process/transformation.py:349-352, :366-368), get_filtered_lidar + makeBEVMap, then
+    torch.flip(bev_map, [-1]) (data_process/kitti_dataset.py:93-97)."""
+    fast = pkg("fast")
+    rng = np.random.default_rng(21)
+    kinds = ["outside", "zties", "uniform", "clustered", "bounds", "outside", "gridaligned"]
+    lens = [30000, 1, 0, 45001, 20000, 120000, 7777]
+    sweeps = [O.synth_sweep(700 + i, n, O.KITTI, k) if n else np.zeros((0, 4), np.float32) for i, (n, k) in enumerate(zip(lens, kinds))]
+    B = len(sweeps)
+    angles = rng.uniform(-np.pi / 4, np.pi / 4, B)
+    factors = rng.uniform(0.95, 1.05, B).astype(np.float32)
+    flips = np.array([0, 1, 1, 0, 1, 1, 0], dtype=np.uint8)
+    offsets = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int64, device=cuda_device)
+    pts = torch.from_numpy(np.concatenate(sweeps)).to(cuda_device)
+    mats = torch.from_numpy(np.stack([np.stack(O.transform_matrices(0, 0, 0, rz=a)) for a in angles])).to(cuda_device)
+    scales = torch.from_numpy(factors).to(cuda_device)
+    hflip = torch.from_numpy(flips).to(cuda_device)
+    rast = fast.BevRasterizer(_geom(O.KITTI), max_batch=B, max_points=max(lens), device=cuda_device)
+    before = pts.clone()
+    got = rast(pts, offsets, max(lens), mats=mats, scales=scales, hflip=hflip).cpu().numpy()
+    assert torch.equal(pts, before)   # the sweep itself is not modified
+    for i, s in enumerate(sweeps):
+        aug = O.random_scaling_points(O.random_rotation_points(s.copy(), angles[i]), factors[i]) if s.shape[0] else s
+        want = O.make_bev_scatter(aug, O.KITTI, True, np.float32)
+        if flips[i]:
+            want = np.ascontiguousarray(np.flip(want, -1))
+        _assert_bit_exact(got[i], want, "augmented frame %d" % i)
+    # each extra alone; hflip only == np.flip of the plain map
+    plain = rast(pts, offsets, max(lens)).cpu().numpy()
+    only_flip = rast(pts, offsets, max(lens), hflip=torch.ones(B, dtype=torch.uint8, device=cuda_device)).cpu().numpy()
+    assert np.array_equal(only_flip.view(np.uint32), np.flip(plain, -1).view(np.uint32))
+    only_rot = rast(pts, offsets, max(lens), mats=mats).cpu().numpy()
+    _assert_bit_exact(only_rot[3], O.make_bev_scatter(O.random_rotation_points(sweeps[3].copy(), angles[3]), O.KITTI, True, np.float32), "rotation only")
+    assert rast.out_of_map_points() == 0
+
+
+def test_bev_front_back_single_pass_many_frames(cuda_device):
+    """Front + back maps from one read of each sweep, more sweeps than half the workspace ring (several chunks), uniform
+    batch form, and a second call on the same workspace."""
+    fast = pkg("fast")
+    rng = np.random.default_rng(5)
+    B, N = 41, 9000
+    pts_np = np.empty((B, N, 4), np.float32)
+    pts_np[..., 0] = rng.uniform(-52, 52, (B, N)); pts_np[..., 1] = rng.uniform(-26, 26, (B, N))
+    pts_np[..., 2] = np.round(rng.uniform(-3, 1.5, (B, N)) * 4) / 4; pts_np[..., 3] = rng.uniform(0, 1, (B, N))
+    pts = torch.from_numpy(pts_np).to(cuda_device)
+    pair = fast.FrontBackRasterizer(max_batch=B, max_points=N, device=cuda_device)
+    for attempt in range(2):
+        front, back = pair(pts.reshape(-1, 4), None, N)
+        f, b = front.cpu().numpy(), back.cpu().numpy()
+        for i in (0, 7, 15, 16, 17, 31, 32, 40):
+            _assert_bit_exact(f[i], O.make_bev_scatter(pts_np[i], O.KITTI, True, np.float32), "front %d" % i)
+            _assert_bit_exact(b[i], O.make_bev_scatter(pts_np[i], O.KITTI_BACK, True, np.float32), "back %d" % i)

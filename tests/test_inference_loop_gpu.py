@@ -91,7 +91,12 @@ def test_full_inference_loop_batch32_reference_model(cuda_device, hm_bias):
         net = TinyBackbone().to(cuda_device).eval()
     with torch.no_grad():
         if hm_bias is not None:
-            net.hm_cen[-1].bias.fill_(hm_bias)
+            # the reference keeps one hm_cen head per FPN level (fpn{0,1,2}_hm_cen, models/fpn_resnet.py:135-145) and
+            # blends them with softmax weights, so the same bias on every level shifts the blended logit by that much
+            hm_heads = [m for name, m in net.named_children() if name.endswith("hm_cen")]
+            assert hm_heads
+            for m in hm_heads:
+                m[-1].bias.fill_(hm_bias)
         out = net(bev)                                   # test.py:149
         hm = tu._sigmoid(out["hm_cen"])                  # test.py:150
         off = tu._sigmoid(out["cen_offset"])             # test.py:151
