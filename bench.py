@@ -409,8 +409,11 @@ def run_b200(args):
     class Engine:
         def __init__(self):
             self.rasts = [fast.BevRasterizer(geom, max_batch=b1 - b0, max_points=N, device=dev) for b0, b1 in lane_frames]
-            self.side = [torch.cuda.Stream(device=dev) for _ in range(lanes)]   # lanes 1.. and the decode
-            self.launch = torch.cuda.Stream(device=dev)
+            # lanes 1.. and (last) the decode, which gets the lower stream priority: its latency-bound kernels fill the
+            # slots the BEV kernels leave instead of competing for them
+            self.side = [torch.cuda.Stream(device=dev, priority=(-1 if (i < lanes - 1 or not args.decode_low_priority) else 0))
+                         for i in range(lanes)]
+            self.launch = torch.cuda.Stream(device=dev, priority=-1)
             self.bev_out = torch.empty((B, 3, BEV_H, BEV_W), dtype=torch.float32, device=dev)
             self.det_out = torch.empty((B, TOPK, 10), dtype=torch.float32, device=dev)
             self.pp_out = (torch.empty((B, TOPK, 8), dtype=torch.float32, device=dev),
@@ -424,8 +427,14 @@ def run_b200(args):
             pts, heads = dev_pts[s % sets], dev_heads[s % sets]
             for i, (b0, b1) in enumerate(lane_frames):
                 self.rasts[i](pts[b0 * N:b1 * N], lane_offsets[i], N, out=self.bev_out[b0:b1])
-            fast.decode_device(*heads, K=TOPK, out=self.det_out, workspace=self.dec_ws)
-            fast.post_process_dense(self.det_out, out=self.pp_out)
+            self.decode(heads)
+
+        def decode(self, heads):
+            if args.separate_post:
+                fast.decode_device(*heads, K=TOPK, out=self.det_out, workspace=self.dec_ws)
+                fast.post_process_dense(self.det_out, out=self.pp_out)
+            else:   # the dense post-processing rows come out of the decode's own epilogue (sfa_decode_post)
+                fast.decode_device(*heads, K=TOPK, out=self.det_out, workspace=self.dec_ws, post=self.pp_out)
 
         def step(self, s):
             if args.eager or (lanes == 1 and not args.decode_stream):
@@ -438,8 +447,7 @@ def run_b200(args):
                 with torch.cuda.stream(main if i == 0 else self.side[i - 1]):
                     self.rasts[i](pts[b0 * N:b1 * N], lane_offsets[i], N, out=self.bev_out[b0:b1])
             with torch.cuda.stream(self.side[-1]):
-                fast.decode_device(*heads, K=TOPK, out=self.det_out, workspace=self.dec_ws)
-                fast.post_process_dense(self.det_out, out=self.pp_out)
+                self.decode(heads)
             for st in self.side:
                 main.wait_stream(st)
 
@@ -560,16 +568,20 @@ def run_b200(args):
     roofline = None
     if dominant and dominant in KB:
         frames_per_launch = B / kern[dominant]["launches_per_step"]
-        traffic, traffic_src = None, None
+        # DRAM bytes of one whole step in THIS schedule (ncu range replay over several overlapped steps: a per-kernel
+        # capture serialises the launches and flushes the L2-resident bucket hand-off between them), profiles/README.md
+        traffic, traffic_src, traffic_alg = None, None, None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tpath):   # ncu capture of this kernel in this configuration (profiles/README.md)
+        if os.path.exists(tpath):
             with open(tpath) as f:
-                ent = json.load(f).get("%s/%s" % (args.config, dominant))
-            if ent and int(ent["frames_per_launch"]) == int(frames_per_launch):
-                traffic, traffic_src = int(ent["dram_bytes_per_launch"]), ent.get("source")
+                ent = json.load(f).get(args.config)
+            if ent and int(ent.get("engines", 0)) == n_pipe and int(ent.get("frames_per_bev_launch", 0)) == int(frames_per_launch):
+                traffic, traffic_src = int(ent["dram_bytes_per_step"]), ent.get("source")
+                traffic_alg = int(ent["algorithmic_bytes_per_step"])
         achieved = KB[dominant] * frames_per_launch / (kern[dominant]["ms_per_launch"] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dominant, "achieved": round(achieved, 1), "peak": hbm_gbs, "unit": "GB/s",
-                    "frac": round(achieved / hbm_gbs, 4), "traffic": traffic, "traffic_source": traffic_src,
+                    "frac": round(achieved / hbm_gbs, 4), "traffic": traffic, "traffic_per": "step (%d frames, all kernels)" % B,
+                    "traffic_algorithmic": traffic_alg, "traffic_source": traffic_src,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": int(KB[dominant] * frames_per_launch),
                     "frames_per_launch": int(frames_per_launch),
                     "timing": "CUDA events around each launch of a serialised, un-captured pass of the same step"}
@@ -803,12 +815,14 @@ def main():
     ap.add_argument("--config", default="headline", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--sets", type=int, default=4)
-    ap.add_argument("--pipelines", type=int, default=2,
+    ap.add_argument("--pipelines", type=int, default=3,
                     help="engines (own workspaces, outputs, streams) that take the steps in turn, so consecutive steps overlap")
-    ap.add_argument("--lanes", type=int, default=2, help="independent BEV streams the batch is split over")
-    ap.add_argument("--decode-stream", action="store_true", help="decode on a stream of its own even with one BEV lane")
+    ap.add_argument("--lanes", type=int, default=1, help="independent BEV streams the batch is split over")
+    ap.add_argument("--decode-stream", type=int, default=1, help="1: the decode runs on a stream of its own next to the BEV lane(s)")
+    ap.add_argument("--decode-low-priority", type=int, default=0, help="1: the decode stream runs at lower priority than the BEV lanes")
     ap.add_argument("--e2e-workers", type=int, default=2, help="host threads of the e2e leg, each with its own pipelines")
     ap.add_argument("--settle-s", type=float, default=0.5, help="seconds of untimed steps before the warm-up (clock ramp, sampler)")
+    ap.add_argument("--separate-post", action="store_true", help="post_processing as its own launch instead of the decode's epilogue")
     ap.add_argument("--ragged-api", action="store_true", help="pass an offsets array instead of the uniform-batch form")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -71,6 +71,9 @@ PROTOTYPES = {
                                 c_void_p, sz, c_void_p]),
     "sfa_decode": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, i32, i32, i32, i32, i32, c_void_p,
                                   c_void_p, i32, c_void_p, sz, c_void_p]),
+    "sfa_decode_post": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, i32, i32, i32, i32, i32, c_void_p,
+                                       c_void_p, i32, i32, f32, f32, f32, f32, f32, f32, f32, f32, f32, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, sz, c_void_p]),
     "sfa_post_process": (ctypes.c_int, [c_void_p, i32, i32, i32, f32, f32, f32, f32, f32, f32, f32, f32, f32, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_void_p]),
     "sfa_transform_points": (ctypes.c_int, [c_void_p, i32, i32, c_void_p, i32, i64, c_void_p, i32, c_void_p, c_void_p, i32,

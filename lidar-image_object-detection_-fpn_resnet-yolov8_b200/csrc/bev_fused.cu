@@ -30,11 +30,20 @@ namespace {
 #define SFA_FUSED_WORKERS 224
 #endif
 constexpr int kFusedWorkers = SFA_FUSED_WORKERS;              // threads that do the arithmetic (multiple of 32, >= 128)
+#ifndef SFA_FUSED_CTAS
+#define SFA_FUSED_CTAS 4
+#endif
+#ifndef SFA_FUSED_NB
+#define SFA_FUSED_NB 128
+#endif
 constexpr int kFusedThreads = kFusedWorkers + 32;             // + the service warp (one active thread)
+constexpr int kFusedPlanBands = SFA_FUSED_NB;                 // bands per frame of the fused schedule (<= kFusedBands)
+// cells per band the shared memory of kFusedCtasPerSm CTAs can hold next to the staging area
+constexpr int kFusedMaxCellsPerBand = SFA_FUSED_CTAS >= 4 ? kMaxCellsPerBand : 2 * kMaxCellsPerBand;
 constexpr int kFusedPoints = 4;                               // points per worker of a bin tile
 constexpr int kFusedTile = kFusedWorkers * kFusedPoints;      // 1024
 constexpr int kFusedBands = 128;
-constexpr int kFusedCtasPerSm = 4;
+constexpr int kFusedCtasPerSm = SFA_FUSED_CTAS;
 constexpr int kFusedMaxRing = 32;
 constexpr int kFusedRegRecords = 6;                           // records a thread keeps in registers across the phases
 constexpr int kFusedSpecRecords = 4;                          // ... of which prefetched before the item starts
@@ -51,7 +60,8 @@ constexpr size_t kFusedCtlBytes = (size_t)(2 + 4 * kFusedMaxRing) * kCtlLine * s
 constexpr size_t kFusedZerosOffset = kZerosOffset;
 static_assert(kFusedWorkers >= kFusedBands && kFusedWorkers % 32 == 0, "one scan thread per band");
 static_assert(kFusedCtlOffset + kFusedCtlBytes <= kFusedZerosOffset, "control block overlaps the zero block");
-static_assert(kFusedZerosOffset + 3 * (size_t)kMaxCellsPerBand * sizeof(uint32_t) <= kHeaderBytes, "zero block does not fit the header");
+static_assert(kFusedZerosOffset + 3 * (size_t)kFusedMaxCellsPerBand * sizeof(uint32_t) <= kHeaderBytes, "zero block does not fit the header");
+static_assert(kFusedPlanBands <= kFusedBands, "one scan thread per band");
 
 struct FusedArgs {
     const float4* pts;
@@ -473,19 +483,39 @@ inline int fused_env(const char* name, int dflt, int lo, int hi) { return env_in
 
 }  // namespace
 
-// Whether a geometry with this band plan can run on the fused kernel.
-bool fused_supported(const BandPlan& plan) { return plan.nb <= kFusedBands && plan.cpb <= kMaxCellsPerBand; }
+// The fused schedule's own band plan (its band count is a tuning constant of this file).
+static bool fused_plan(const SfaBevParams* p, BandPlan* plan) {
+    return plan_bands(p->height, p->width, plan, kFusedMaxCellsPerBand, kFusedPlanBands) && plan->nb <= kFusedBands &&
+           plan->cpb <= kFusedMaxCellsPerBand;
+}
+// Whether this geometry can run on the fused kernel.
+bool fused_supported(const SfaBevParams* p) {
+    BandPlan plan;
+    return fused_plan(p, &plan);
+}
 // What SFA_BEV_AUTO picks among the two tiled schedules (SFA_BEV_FUSED=0/1 overrides).
 bool fused_is_default() {
     static const int enabled = env_int("SFA_BEV_FUSED", 0, 0, 1);
     return enabled != 0;
 }
 
-// Enqueue all B frames as ONE launch.  Workspace layout as the two-kernel tiled path (header | cursors | ring slots).
-int fused_launch(const float* pts, const int64_t* offsets, int B, int64_t max_points, const SfaBevParams* p,
-                 const BandPlan& plan, const float* lut, float* out, uint32_t* status, unsigned char* ws_base,
-                 uint32_t* cursors, BevRecord* buckets, size_t slot_recs, uint32_t bucket_cap, int ring_avail,
-                 cudaStream_t stream) {
+// Enqueue all B frames as ONE launch.  ws_base: the workspace (header | cursors | ring slots of `slots_bytes`).
+int fused_launch(const float* pts, const int64_t* offsets, int B, int64_t max_points, const SfaBevParams* p, const float* lut,
+                 float* out, uint32_t* status, unsigned char* ws_base, uint32_t* cursors, unsigned char* slots,
+                 size_t slots_bytes, cudaStream_t stream) {
+    BandPlan plan;
+    if (!fused_plan(p, &plan)) {
+        set_error("geometry not supported by the fused kernel");
+        return SFA_ERR_UNSUPPORTED;
+    }
+    const size_t slot_recs = slot_records(max_points, plan.nb);
+    const uint32_t bucket_cap = (uint32_t)bucket_records(max_points, plan.nb);
+    const int ring_avail = (int)(slots_bytes / (slot_recs * sizeof(BevRecord)));
+    if (ring_avail < 1) {
+        set_error("workspace too small for the fused schedule");
+        return SFA_ERR_WORKSPACE_TOO_SMALL;
+    }
+    BevRecord* buckets = reinterpret_cast<BevRecord*>(slots);
     static const int ring_want = fused_env("SFA_BEV_FUSED_RING", 16, 2, kFusedMaxRing);
     static const int lag_want = fused_env("SFA_BEV_FUSED_LAG", 10, 1, kFusedMaxRing - 1);
     FusedArgs a;
@@ -515,7 +545,8 @@ int fused_launch(const float* pts, const int64_t* offsets, int B, int64_t max_po
     const int ctas = (int)(items < (long long)kFusedCtasPerSm * kNumSMs ? items : (long long)kFusedCtasPerSm * kNumSMs);
     const size_t inv_bytes = (size_t)plan.cpb * 4 > kFusedStageBytes ? (size_t)plan.cpb * 4 : kFusedStageBytes;
     const size_t smem = 3 * (size_t)plan.cpb * 4 + inv_bytes;
-    const size_t max_smem = 3 * (size_t)kMaxCellsPerBand * 4 + kFusedStageBytes;
+    const size_t max_smem = 3 * (size_t)kFusedMaxCellsPerBand * 4 +
+                            ((size_t)kFusedMaxCellsPerBand * 4 > kFusedStageBytes ? (size_t)kFusedMaxCellsPerBand * 4 : kFusedStageBytes);
     int exp2 = 0;
     const float mant = frexpf(fabsf(a.g.max_h), &exp2);
     const bool mul_height = (mant == 0.5f) && exp2 > -120 && exp2 < 120 && a.g.max_h > 0.0f;

@@ -72,6 +72,10 @@ struct DecodeArgs {
     int64_t* inds;        // [B,K] or null
     // _topk outputs (all null for decode)
     float* tk_score; int32_t* tk_cls; float* tk_ys; float* tk_xs;
+    // dense post_processing fused behind the decode (sfa_decode_post; pp_rows null = off)
+    float* pp_rows; int32_t* pp_cls; uint8_t* pp_keep; float* pp_real;
+    int pp_num_classes;
+    float pp_down_ratio, pp_bsy, pp_bev_w, pp_bsx, pp_bev_h, pp_thresh, pp_min_x, pp_min_y, pp_min_z;
 };
 
 // _sigmoid of utils/torch_utils.py:44-45: clamp(sigmoid(x), 1e-4, 1 - 1e-4).  The clamp bounds are the
@@ -431,6 +435,41 @@ __device__ void block_radix_select(WordFn word, int n, unsigned need, SelectShar
     }
 }
 
+// convert_det_to_real_values, evaluation_utils.py:177-193: one post_processing row (score, x, y, z, h, w, l, yaw
+// in BEV pixels) -> metres in the lidar frame, [cls, x, y, z, h, w, l, yaw]; every step rounds to fp32 like
+// numpy's float32 scalars
+__device__ __forceinline__ void real_values_row(const float* __restrict__ o, float cls, float bsy, float bev_w, float bsx,
+                                                float bev_h, float min_x, float min_y, float min_z, float* __restrict__ r) {
+    r[0] = cls;
+    r[1] = __fadd_rn(__fmul_rn(__fdiv_rn(o[2], bev_h), bsx), min_x);   // x <- y pixel, :185
+    r[2] = __fadd_rn(__fmul_rn(__fdiv_rn(o[1], bev_w), bsy), min_y);   // y <- x pixel, :186
+    r[3] = __fadd_rn(o[3], min_z);                                     // :187
+    r[4] = o[4];
+    r[5] = __fmul_rn(__fdiv_rn(o[5], bev_w), bsy);                     // :188
+    r[6] = __fmul_rn(__fdiv_rn(o[6], bev_h), bsx);                     // :189
+    r[7] = -o[7];                                                      // :184
+}
+
+// One dense post_processing row (utils/evaluation_utils.py:112-163) from one detection d[10].
+__device__ __forceinline__ void post_row(const float* d, int num_classes, float down_ratio, float bsy, float bev_w, float bsx,
+                                         float bev_h, float thresh, float min_x, float min_y, float min_z, float* __restrict__ o,
+                                         int32_t* __restrict__ cls, uint8_t* __restrict__ keep, float* __restrict__ real) {
+    const float score = d[0];
+    o[0] = score;
+    o[1] = __fmul_rn(d[1], down_ratio);                      // evaluation_utils.py:138
+    o[2] = __fmul_rn(d[2], down_ratio);                      // :139
+    o[3] = d[3];
+    o[4] = d[4];
+    o[5] = __fmul_rn(__fdiv_rn(d[5], bsy), bev_w);           // :142  (divide, then multiply)
+    o[6] = __fmul_rn(__fdiv_rn(d[6], bsx), bev_h);           // :143
+    o[7] = atan2f(d[7], d[8]);                               // :108-109, :144
+    const float cf = d[9];
+    const int c = (cf >= 0.0f && cf < (float)num_classes && cf == floorf(cf)) ? (int)cf : -1;
+    *cls = c;
+    *keep = (c >= 0 && score > thresh) ? 1 : 0;              // :134, :152
+    if (real) real_values_row(o, cf, bsy, bev_w, bsx, bev_h, min_x, min_y, min_z, real);
+}
+
 __global__ void __launch_bounds__(kSelThreads)
 peak_select_kernel(DecodeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -586,23 +625,38 @@ peak_select_kernel(DecodeArgs a) {
             a.tk_xs[o] = (float)x;   // (ind % w).int().float(), :54
         }
         if (a.det) {
-            float xs, ys;
-            if (a.off) {
-                const float* ob = a.off + (size_t)b * 2 * hw;
-                xs = __fadd_rn((float)x, act(ob[sp], a.apply_sigmoid != 0));        // :85
-                ys = __fadd_rn((float)y, act(ob[hw + sp], a.apply_sigmoid != 0));   // :86
-            } else {
-                xs = __fadd_rn((float)x, 0.5f);          // :88-89
-                ys = __fadd_rn((float)y, 0.5f);
-            }
+            // All eight gathers are issued before anything depends on them: written as `d[3] = zb[sp]; d[4] = ...` each
+            // store waits for its own load and, issue being in order, holds back the next load — eight serialised trips
+            // to HBM (the regression heads are read nowhere else) were 40 % of this kernel.
             const float* db = a.dir + (size_t)b * 2 * hw;
             const float* zb = a.zc + (size_t)b * hw;
             const float* mb = a.dim + (size_t)b * 3 * hw;
+            float ox = 0.5f, oy = 0.5f;                  // :88-89 when there is no offset head
+            if (a.off) {
+                const float* ob = a.off + (size_t)b * 2 * hw;
+                ox = __ldg(ob + sp);
+                oy = __ldg(ob + hw + sp);
+            }
+            const float vz = __ldg(zb + sp);
+            const float m0 = __ldg(mb + sp), m1 = __ldg(mb + hw + sp), m2 = __ldg(mb + 2 * hw + sp);
+            const float d0 = __ldg(db + sp), d1 = __ldg(db + hw + sp);
+            if (a.off) {
+                ox = act(ox, a.apply_sigmoid != 0);
+                oy = act(oy, a.apply_sigmoid != 0);
+            }
+            const float xs = __fadd_rn((float)x, ox);    // :85
+            const float ys = __fadd_rn((float)y, oy);    // :86
             float* d = a.det + o * 10;                   // :103 column order
-            d[0] = score; d[1] = xs; d[2] = ys; d[3] = zb[sp];
-            d[4] = mb[sp]; d[5] = mb[hw + sp]; d[6] = mb[2 * hw + sp];
-            d[7] = db[sp]; d[8] = db[hw + sp];
+            d[0] = score; d[1] = xs; d[2] = ys; d[3] = vz;
+            d[4] = m0; d[5] = m1; d[6] = m2;
+            d[7] = d0; d[8] = d1;
             d[9] = (float)c;
+            if (a.pp_rows) {   // dense post_processing of the row, from registers
+                const float row[10] = {score, xs, ys, vz, m0, m1, m2, d0, d1, (float)c};
+                post_row(row, a.pp_num_classes, a.pp_down_ratio, a.pp_bsy, a.pp_bev_w, a.pp_bsx, a.pp_bev_h, a.pp_thresh,
+                         a.pp_min_x, a.pp_min_y, a.pp_min_z, a.pp_rows + o * 8, a.pp_cls + o, a.pp_keep + o,
+                         a.pp_real ? a.pp_real + o * 8 : nullptr);
+            }
         }
     }
 }
@@ -633,21 +687,6 @@ nms_kernel(const float* __restrict__ heat, int planes, int h, int w, float* __re
     }
 }
 
-// convert_det_to_real_values, evaluation_utils.py:177-193: one post_processing row (score, x, y, z, h, w, l, yaw
-// in BEV pixels) -> metres in the lidar frame, [cls, x, y, z, h, w, l, yaw]; every step rounds to fp32 like
-// numpy's float32 scalars
-__device__ __forceinline__ void real_values_row(const float* __restrict__ o, float cls, float bsy, float bev_w, float bsx,
-                                                float bev_h, float min_x, float min_y, float min_z, float* __restrict__ r) {
-    r[0] = cls;
-    r[1] = __fadd_rn(__fmul_rn(__fdiv_rn(o[2], bev_h), bsx), min_x);   // x <- y pixel, :185
-    r[2] = __fadd_rn(__fmul_rn(__fdiv_rn(o[1], bev_w), bsy), min_y);   // y <- x pixel, :186
-    r[3] = __fadd_rn(o[3], min_z);                                     // :187
-    r[4] = o[4];
-    r[5] = __fmul_rn(__fdiv_rn(o[5], bev_w), bsy);                     // :188
-    r[6] = __fmul_rn(__fdiv_rn(o[6], bev_h), bsx);                     // :189
-    r[7] = -o[7];                                                      // :184
-}
-
 __global__ void __launch_bounds__(128)
 real_values_kernel(const float* __restrict__ rows, const int32_t* __restrict__ cls, int n, float bsy, float bev_w, float bsx,
                    float bev_h, float min_x, float min_y, float min_z, float* __restrict__ real) {
@@ -663,24 +702,8 @@ post_process_kernel(const float* __restrict__ det, int n, int num_classes, float
                     float* __restrict__ real) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float* d = det + (size_t)i * 10;
-    float* o = out + (size_t)i * 8;
-    float score = d[0];
-    o[0] = score;
-    o[1] = __fmul_rn(d[1], down_ratio);                      // evaluation_utils.py:138
-    o[2] = __fmul_rn(d[2], down_ratio);                      // :139
-    o[3] = d[3];
-    o[4] = d[4];
-    o[5] = __fmul_rn(__fdiv_rn(d[5], bsy), bev_w);           // :142  (divide, then multiply)
-    o[6] = __fmul_rn(__fdiv_rn(d[6], bsx), bev_h);           // :143
-    o[7] = atan2f(d[7], d[8]);                               // :108-109, :144
-    float cf = d[9];
-    int c = (cf >= 0.0f && cf < (float)num_classes && cf == floorf(cf)) ? (int)cf : -1;
-    cls[i] = c;
-    keep[i] = (c >= 0 && score > thresh) ? 1 : 0;            // :134, :152
-    if (real) {
-        real_values_row(o, cf, bsy, bev_w, bsx, bev_h, min_x, min_y, min_z, real + (size_t)i * 8);
-    }
+    post_row(det + (size_t)i * 10, num_classes, down_ratio, bsy, bev_w, bsx, bev_h, thresh, min_x, min_y, min_z,
+             out + (size_t)i * 8, cls + i, keep + i, real ? real + (size_t)i * 8 : nullptr);
 }
 
 size_t decode_workspace_bytes(int B, int C, int h, int w) {
@@ -755,6 +778,26 @@ extern "C" int sfa_decode(const float* hm, const float* cen_offset, const float*
     a.do_nms = 1;
     a.apply_sigmoid = apply_sigmoid ? 1 : 0;
     a.det = det; a.inds = inds;
+    return launch_decode(a, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int sfa_decode_post(const float* hm, const float* cen_offset, const float* direction, const float* z_coor,
+                               const float* dim, int32_t B, int32_t C, int32_t h, int32_t w, int32_t K, float* det,
+                               int64_t* inds, int32_t apply_sigmoid, int32_t num_classes, float down_ratio,
+                               float bound_size_y, float bev_width, float bound_size_x, float bev_height, float peak_thresh,
+                               float min_x, float min_y, float min_z, float* rows, int32_t* cls, uint8_t* keep, float* real,
+                               void* workspace, size_t workspace_bytes, sfa_stream_t stream) {
+    SFA_REQUIRE(B == 0 || (hm && direction && z_coor && dim && det && rows && cls && keep), "NULL pointer argument");
+    DecodeArgs a = {};
+    a.hm = hm; a.off = cen_offset; a.dir = direction; a.zc = z_coor; a.dim = dim;
+    a.B = B; a.C = C; a.h = h; a.w = w; a.K = K;
+    a.do_nms = 1;
+    a.apply_sigmoid = apply_sigmoid ? 1 : 0;
+    a.det = det; a.inds = inds;
+    a.pp_rows = rows; a.pp_cls = cls; a.pp_keep = keep; a.pp_real = real;
+    a.pp_num_classes = num_classes; a.pp_down_ratio = down_ratio; a.pp_bsy = bound_size_y; a.pp_bev_w = bev_width;
+    a.pp_bsx = bound_size_x; a.pp_bev_h = bev_height; a.pp_thresh = peak_thresh;
+    a.pp_min_x = min_x; a.pp_min_y = min_y; a.pp_min_z = min_z;
     return launch_decode(a, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 

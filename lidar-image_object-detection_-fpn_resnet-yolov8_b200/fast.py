@@ -233,12 +233,14 @@ class DecodeWorkspace:
 
 
 def decode_device(hm_cen, cen_offset, direction, z_coor, dim, K=40, out=None, inds=None, workspace=None,
-                  apply_sigmoid=False):
+                  apply_sigmoid=False, post=None, post_params=None):
     """decode (utils/evaluation_utils.py:77-105) on CUDA float32 NCHW-contiguous heads, writing into
     `out` [B,K,10] (allocated when None) — no allocation, copy or sync when `out` is given, so the
     call can be captured in a CUDA graph.  `inds` optional int64 [B,K] receives the spatial indices.
     apply_sigmoid=True takes the backbone's RAW hm_cen / cen_offset logits and applies `_sigmoid`
-    (utils/torch_utils.py:44-45) while loading them (tolerance-level parity, see include/sfa_b200.h)."""
+    (utils/torch_utils.py:44-45) while loading them (tolerance-level parity, see include/sfa_b200.h).
+    post=(rows [B,K,8] f32, cls [B,K] i32, keep [B,K] u8[, real [B,K,8] f32]): also writes the dense post_processing of
+    the detections in the same launches (sfa_decode_post); post_params = dict(num_classes, down_ratio, peak_thresh, cnf)."""
     lib = _lib.load()
     for name, t in (("hm_cen", hm_cen), ("direction", direction), ("z_coor", z_coor), ("dim", dim)):
         _require_cuda(t, name)
@@ -259,9 +261,26 @@ def decode_device(hm_cen, cen_offset, direction, z_coor, dim, K=40, out=None, in
     else:
         ws_ptr, ws_bytes = decode_workspace(hm_cen.device, B, C, h, w, K)
     with torch.cuda.device(hm_cen.device):
-        rc = lib.sfa_decode(_ptr(hm_cen), _ptr(cen_offset), _ptr(direction), _ptr(z_coor), _ptr(dim), B, C, h, w, K,
-                            _ptr(out), _ptr(inds), 1 if apply_sigmoid else 0, ctypes.c_void_p(ws_ptr), ws_bytes,
-                            _stream_ptr(hm_cen.device))
+        if post is None:
+            rc = lib.sfa_decode(_ptr(hm_cen), _ptr(cen_offset), _ptr(direction), _ptr(z_coor), _ptr(dim), B, C, h, w, K,
+                                _ptr(out), _ptr(inds), 1 if apply_sigmoid else 0, ctypes.c_void_p(ws_ptr), ws_bytes,
+                                _stream_ptr(hm_cen.device))
+        else:
+            from .config import kitti_config
+            pp = dict(post_params or {})
+            cnf = pp.get("cnf") or kitti_config
+            rows, cls, keep = post[0], post[1], post[2]
+            real = post[3] if len(post) > 3 else None
+            if (rows.shape != (B, K, 8) or rows.dtype != torch.float32 or cls.shape != (B, K) or cls.dtype != torch.int32 or
+                    keep.shape != (B, K) or keep.dtype != torch.uint8 or not (rows.is_contiguous() and cls.is_contiguous() and keep.is_contiguous())):
+                raise ValueError("post must be (rows [B,K,8] f32, cls [B,K] i32, keep [B,K] u8[, real [B,K,8] f32]), contiguous")
+            bd = cnf.boundary
+            rc = lib.sfa_decode_post(_ptr(hm_cen), _ptr(cen_offset), _ptr(direction), _ptr(z_coor), _ptr(dim), B, C, h, w, K,
+                                     _ptr(out), _ptr(inds), 1 if apply_sigmoid else 0, int(pp.get("num_classes", 3)),
+                                     float(pp.get("down_ratio", 4)), float(cnf.bound_size_y), float(cnf.BEV_WIDTH),
+                                     float(cnf.bound_size_x), float(cnf.BEV_HEIGHT), float(pp.get("peak_thresh", 0.2)),
+                                     float(bd["minX"]), float(bd["minY"]), float(bd["minZ"]), _ptr(rows), _ptr(cls), _ptr(keep),
+                                     _ptr(real), ctypes.c_void_p(ws_ptr), ws_bytes, _stream_ptr(hm_cen.device))
     if rc != 0:
         # torch.topk raises RuntimeError when K > h*w (evaluation_utils.py:50): same exception type
         raise RuntimeError("decode: " + _lib.last_error())

@@ -520,3 +520,25 @@ def test_bev_front_back_single_pass_many_frames(cuda_device):
         for i in (0, 7, 15, 16, 17, 31, 32, 40):
             _assert_bit_exact(f[i], O.make_bev_scatter(pts_np[i], O.KITTI, True, np.float32), "front %d" % i)
             _assert_bit_exact(b[i], O.make_bev_scatter(pts_np[i], O.KITTI_BACK, True, np.float32), "back %d" % i)
+
+
+def test_stream8192_shard_frames(cuda_device):
+    """BASELINE config[4] (bench.py --config stream8192): the sweeps of the 8192-frame stream are generated on the device
+    from their frame number and sharded frame i -> rank i mod G.  Frames of one rank's shard: reproducible from the
+    frame id alone (whatever the rank / batch position), and their maps bit-exact against the oracle."""
+    import bench
+    fast, sharding = pkg("fast"), pkg("sharding")
+    shard = list(sharding.shard_range(8192, 1, 4, "cyclic"))
+    assert shard[:3] == [1, 5, 9] and len(shard) == 2048
+    ids = shard[:3] + [shard[-1]]
+    N = 120000
+    pts = bench.stream_frames_device(ids, N, cuda_device, torch)
+    again = bench.stream_frames_device([ids[-1], ids[0]], N, cuda_device, torch)
+    assert torch.equal(again[0], pts[-1]) and torch.equal(again[1], pts[0])
+    rast = fast.BevRasterizer(_geom(O.KITTI), max_batch=len(ids), max_points=N, device=cuda_device)
+    got = rast.rasterize_uniform(pts).cpu().numpy()
+    host = pts.cpu().numpy()
+    b = O.KITTI.boundary
+    assert host[..., 0].min() >= b["minX"] and host[..., 0].max() <= b["maxX"] and host[..., 2].min() >= b["minZ"] - 1e-6
+    for i in range(len(ids)):
+        _assert_bit_exact(got[i], O.make_bev_scatter(host[i], O.KITTI, True, np.float32), "stream frame %d" % ids[i])

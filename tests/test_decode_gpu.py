@@ -377,3 +377,29 @@ def test_decode_with_nan_and_inf_cells(cuda_device):
         key = lambda rows: rows[np.lexsort((rows[:, 2], rows[:, 1], rows[:, 9]))][:, 1:]
         assert np.array_equal(key(got[b][g_nan]), key(want[b][w_nan]))
     assert np.isinf(got[0, 3, 0]) and np.isinf(got[1, 0, 0])
+
+
+def test_decode_with_fused_post_processing(cuda_device):
+    """sfa_decode_post: the dense post_processing rows written by the decode's own epilogue equal the stand-alone
+    sfa_post_process of the same detections bit for bit (same device function), detections unchanged."""
+    fast = pkg("fast")
+    heads = [t.to(cuda_device) for t in O.synth_heads(91, B=5)]
+    B, K = 5, 50
+    det0 = fast.decode_device(*heads, K=K)
+    rows0, cls0, keep0, real0 = fast.post_process_dense(det0, real=True)
+    det1 = torch.empty_like(det0)
+    post = (torch.empty((B, K, 8), device=cuda_device), torch.empty((B, K), dtype=torch.int32, device=cuda_device),
+            torch.empty((B, K), dtype=torch.uint8, device=cuda_device), torch.empty((B, K, 8), device=cuda_device))
+    fast.decode_device(*heads, K=K, out=det1, post=post)
+    torch.cuda.synchronize()
+    assert torch.equal(det0, det1)
+    assert torch.equal(rows0.view(torch.int32), post[0].view(torch.int32)) and torch.equal(cls0, post[1])
+    assert torch.equal(keep0, post[2].bool()) and torch.equal(real0.view(torch.int32), post[3].view(torch.int32))
+    ref = O.post_processing(det0.cpu().numpy().astype(np.float32))
+    r, c, k = post[0].cpu().numpy(), post[1].cpu().numpy(), post[2].cpu().numpy().astype(bool)
+    for i in range(B):
+        for j in range(3):
+            w = np.asarray(ref[i][j], np.float32).reshape(-1, 8)
+            g = r[i][(c[i] == j) & k[i]]
+            assert g.shape == w.shape and np.array_equal(g[:, :7], w[:, :7])
+            np.testing.assert_allclose(g[:, 7], w[:, 7], rtol=1e-5, atol=1e-6)

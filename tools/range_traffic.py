@@ -3,7 +3,9 @@
 cudaProfilerStart/Stop.  Run under
     ncu --replay-mode range --profile-from-start off --cache-control none --clock-control none \
         --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum python tools/range_traffic.py <algorithm> [steps]
-Usage: range_traffic.py [algorithm=0] [steps_in_range=1]"""
+With engines > 1 the steps are dealt round-robin to that many independent engines (own rasteriser workspace, outputs and
+CUDA stream), like bench.py's --pipelines: the range then holds the overlapped schedule the benchmark times.
+Usage: range_traffic.py [algorithm=0] [steps_in_range=1] [engines=1]"""
 import importlib, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -14,6 +16,7 @@ fast = importlib.import_module(P + ".fast"); geometry = importlib.import_module(
 cnf = importlib.import_module(P + ".config.kitti_config")
 algo = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+n_eng = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 dev = torch.device("cuda", 0)
 B, N = 64, 120000
 rng = np.random.default_rng(0)
@@ -24,19 +27,28 @@ def sweeps():
     return torch.from_numpy(a).to(dev)
 sets = [sweeps() for _ in range(3)]
 heads = [tuple(t.to(dev) for t in O.synth_heads(7 + i, B=B)) for i in range(3)]
-rast = fast.BevRasterizer(geometry.from_config(cnf, algorithm=algo), max_batch=B, max_points=N, device=dev)
-bev = torch.empty((B, 3, 608, 608), device=dev)
-det = torch.empty((B, 50, 10), device=dev)
-pp = (torch.empty((B, 50, 8), device=dev), torch.empty((B, 50), dtype=torch.int32, device=dev), torch.empty((B, 50), dtype=torch.uint8, device=dev))
-ws = fast.DecodeWorkspace(dev, B, 3, 152, 152, 50)
-def step(i):
-    rast.rasterize_uniform(sets[i % 3], out=bev)
-    fast.decode_device(*heads[i % 3], K=50, out=det, workspace=ws)
-    fast.post_process_dense(det, out=pp)
-for i in range(4): step(i)
+class Engine:
+    def __init__(self):
+        self.rast = fast.BevRasterizer(geometry.from_config(cnf, algorithm=algo), max_batch=B, max_points=N, device=dev)
+        self.bev = torch.empty((B, 3, 608, 608), device=dev)
+        self.det = torch.empty((B, 50, 10), device=dev)
+        self.pp = (torch.empty((B, 50, 8), device=dev), torch.empty((B, 50), dtype=torch.int32, device=dev),
+                   torch.empty((B, 50), dtype=torch.uint8, device=dev))
+        self.ws = fast.DecodeWorkspace(dev, B, 3, 152, 152, 50)
+        self.stream = torch.cuda.Stream(device=dev)
+
+    def step(self, i):
+        with torch.cuda.stream(self.stream):
+            self.rast.rasterize_uniform(sets[i % 3], out=self.bev)
+            fast.decode_device(*heads[i % 3], K=50, out=self.det, workspace=self.ws, post=self.pp)
+
+
+engines = [Engine() for _ in range(n_eng)]
+torch.cuda.synchronize()
+for i in range(2 * n_eng + 2): engines[i % n_eng].step(i)
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
-for i in range(steps): step(4 + i)
+for i in range(steps): engines[i % n_eng].step(4 + i)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
-print("range of %d step(s) done, algorithm %d" % (steps, algo))
+print("range of %d step(s) on %d engine(s) done, algorithm %d" % (steps, n_eng, algo))
