@@ -425,9 +425,11 @@ def run_b200(args):
         def step_serial(self, s):
             """Same launches as step(), all on the current stream (per-kernel event timing, ncu)."""
             pts, heads = dev_pts[s % sets], dev_heads[s % sets]
-            for i, (b0, b1) in enumerate(lane_frames):
-                self.rasts[i](pts[b0 * N:b1 * N], lane_offsets[i], N, out=self.bev_out[b0:b1])
-            self.decode(heads)
+            if args.only != "decode":
+                for i, (b0, b1) in enumerate(lane_frames):
+                    self.rasts[i](pts[b0 * N:b1 * N], lane_offsets[i], N, out=self.bev_out[b0:b1])
+            if args.only != "bev":
+                self.decode(heads)
 
         def decode(self, heads):
             if args.separate_post:
@@ -443,11 +445,13 @@ def run_b200(args):
             main = torch.cuda.current_stream(dev)
             for st in self.side:
                 st.wait_stream(main)
-            for i, (b0, b1) in enumerate(lane_frames):
-                with torch.cuda.stream(main if i == 0 else self.side[i - 1]):
-                    self.rasts[i](pts[b0 * N:b1 * N], lane_offsets[i], N, out=self.bev_out[b0:b1])
-            with torch.cuda.stream(self.side[-1]):
-                self.decode(heads)
+            if args.only != "decode":
+                for i, (b0, b1) in enumerate(lane_frames):
+                    with torch.cuda.stream(main if i == 0 else self.side[i - 1]):
+                        self.rasts[i](pts[b0 * N:b1 * N], lane_offsets[i], N, out=self.bev_out[b0:b1])
+            if args.only != "bev":
+                with torch.cuda.stream(self.side[-1]):
+                    self.decode(heads)
             for st in self.side:
                 main.wait_stream(st)
 
@@ -591,7 +595,7 @@ def run_b200(args):
 
     # ---- e2e: host buffers through the host-pipeline C ABI ------------------------------------------
     e2e = None
-    if not args.no_e2e and host_sets is not None:
+    if not args.no_e2e and host_sets is not None and args.only == "both":
         e2e = run_e2e(args, torch, dist, dev, local_rank, world, fast, geom, host_sets[0], B, N, engines[0], barrier)
 
     if rank == 0:
@@ -601,7 +605,8 @@ def run_b200(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": (wl["what"] % {"B": B, "N": N}) + " -> %d x [3,608,608] BEV + _nms/_topk/decode K=%d on [%d,%d,%d] heads "
                                    "+ dense post_processing, per GPU per step" % (B, TOPK, HEAD_C, HEAD_H, HEAD_W),
-                       "name": args.config, "frames_per_step_per_gpu": B,
+                       "name": args.config if args.only == "both" else "%s (ABLATION: %s stage only)" % (args.config, args.only),
+                       "frames_per_step_per_gpu": B,
                        "l2_policy": "inputs rotate over %d distinct batches (%.0f MB) > L2" %
                        (sets, sets * B * (16 * N + 44 * HEAD_H * HEAD_W) / 1e6),
                        "cuda_graph": not args.eager, "settle_steps_before_warmup": n_settle,
@@ -815,13 +820,15 @@ def main():
     ap.add_argument("--config", default="headline", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--sets", type=int, default=4)
-    ap.add_argument("--pipelines", type=int, default=3,
+    ap.add_argument("--pipelines", type=int, default=2,
                     help="engines (own workspaces, outputs, streams) that take the steps in turn, so consecutive steps overlap")
     ap.add_argument("--lanes", type=int, default=1, help="independent BEV streams the batch is split over")
     ap.add_argument("--decode-stream", type=int, default=1, help="1: the decode runs on a stream of its own next to the BEV lane(s)")
     ap.add_argument("--decode-low-priority", type=int, default=0, help="1: the decode stream runs at lower priority than the BEV lanes")
     ap.add_argument("--e2e-workers", type=int, default=2, help="host threads of the e2e leg, each with its own pipelines")
     ap.add_argument("--settle-s", type=float, default=0.5, help="seconds of untimed steps before the warm-up (clock ramp, sampler)")
+    ap.add_argument("--only", default="both", choices=["both", "bev", "decode"],
+                    help="ablation: time one stage alone in the same schedule (the printed value is then NOT the metric)")
     ap.add_argument("--separate-post", action="store_true", help="post_processing as its own launch instead of the decode's epilogue")
     ap.add_argument("--ragged-api", action="store_true", help="pass an offsets array instead of the uniform-batch form")
     ap.add_argument("--no-e2e", action="store_true")
