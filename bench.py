@@ -16,7 +16,7 @@ Configs (BASELINE.json `configs`):
               (sharding.shard_range(..., "cyclic")), device-resident, processed in 64-frame batches; one step = one
               batch of the rank's shard, the default step count covers the whole stream once.
   loop32      configs[2]: the full inference loop at batch 32 — GPU BEV -> the reference's random-init fpn_resnet_18
-              (stock PyTorch, from the git-ignored oracle/_ref copy) -> _sigmoid -> GPU decode -> post-processing;
+              (stock PyTorch, from the git-ignored baseline/_ref copy) -> _sigmoid -> GPU decode -> post-processing;
               end-to-end frames/s and the hot path's share of the step by CUDA events.
 N > 1: every rank runs the same per-GPU batch on its own frames (weak scaling; frames shard with no collective on the
 data path).
@@ -29,7 +29,7 @@ ONE JSON line (rank 0):
   roofline     dominant kernel: algorithmic bytes per launch / CUDA-event duration of that launch, measured live in a
                separate un-captured pass with events around every library launch; `traffic` = DRAM bytes per launch of
                that kernel in this configuration from the committed ncu capture (profiles/roofline_traffic.json).
-  cpu_baseline the reference's own functions (oracle/_ref copy; the oracle port when absent) on the host cores of this
+  cpu_baseline the reference's own functions (baseline/_ref copy; the oracle port when absent) on the host cores of this
                box, bounded sample (N=1 only), plus a one-process one-thread figure.
 """
 import argparse
@@ -129,7 +129,7 @@ def synth_sweeps(seed, batch, n_points, geom, dist):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: one frame = filter -> makeBEVMap -> .float() -> decode (B=1, as every reference script calls
 # it) -> post_processing.  kind "reference": the reference's own, unmodified functions
-# from the oracle/_ref copy; kind "port": the oracle's restatement (only where that copy is absent).
+# from the baseline/_ref copy; kind "port": the oracle's restatement (only where that copy is absent).
 # ------------------------------------------------------------------------------------------------
 def reference_kind():
     import ref_loader
@@ -237,7 +237,7 @@ def cpu_baseline_block(wl, batch, steps, warmup, budget_s):
     f1, t1, _ = run_cpu_arm(wl, steps=1, warmup=0, batch=8, kind=kind, workers=1, budget_s=8.0)
     v1 = f1 * len(t1) / sum(t1)
     what = ("the reference's own get_filtered_lidar + makeBEVMap + .float() + decode(B=1, K=%d) + post_processing (unmodified, "
-            "imported from the oracle/_ref copy)" % TOPK if kind == "reference" else
+            "imported from the baseline/_ref copy)" % TOPK if kind == "reference" else
             "oracle port of get_filtered_lidar + makeBEVMap (numpy lexsort+unique) + .float() + decode(B=1, K=%d, torch max_pool2d+topk) "
             "+ post_processing (reference copy absent)" % TOPK)
     return {"value": round(v, 2), "unit": "frames/s", "cores": cores, "kind": kind, "cpu": cpu_model_name(),
@@ -709,11 +709,11 @@ def run_e2e(args, torch, dist, dev, local_rank, world, fast, geom, host_set, B, 
 def run_loop32(args, torch, dev, fast, geom, dev_pts, B, N, sets, cpu_baseline, bytes_frame, lib):
     """BASELINE configs[2]: sweeps -> GPU BEV -> the reference's own fpn_resnet_18 (random init; the backbone is out of
     scope and stays stock PyTorch) -> _sigmoid -> GPU decode -> dense post-processing, batch 32, all on one stream.
-    The reference network is the checker-side copy (oracle/_ref, see oracle/ref_loader.py): it is not product code."""
+    The reference network is the checker-side copy (baseline/_ref, see oracle/ref_loader.py): it is not product code."""
     import ref_loader
     if not ref_loader.available():
         emit({"metric": "BEV+decode frames/s", "config": {"name": "loop32"}, "unavailable":
-              "the reference's fpn_resnet_18 is not present (oracle/_ref/sfa is made by __graft_entry__.build() where /root/reference exists)"})
+              "the reference's fpn_resnet_18 is not present (baseline/_ref/sfa is made by __graft_entry__.build() where /root/reference exists)"})
         return
     tu = pkg("utils.torch_utils")
     net = ref_loader.create_model("fpn_resnet_18", seed=0).to(dev)
@@ -771,7 +771,7 @@ def run_loop32(args, torch, dev, fast, geom, dev_pts, B, N, sets, cpu_baseline, 
 
 
 def run_reference(args):
-    """The reference's own implementation of the path on all host cores (oracle/_ref copy of its Python packages; the
+    """The reference's own implementation of the path on all host cores (baseline/_ref copy of its Python packages; the
     oracle port only where that copy is absent).  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

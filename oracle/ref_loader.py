@@ -7,10 +7,11 @@ bench.py's `--impl reference` / `cpu_baseline` legs.  The product never imports 
 Where the reference comes from, first hit wins:
   1. $SFA_REFERENCE_ROOT
   2. /root/reference                      (build container only; read in place)
-  3. <repo>/oracle/_ref/sfa               (git-ignored copy made by install(), i.e. by
+  3. <repo>/baseline/_ref/sfa               (git-ignored copy made by install(), i.e. by
                                            `python oracle/ref_loader.py install` or __graft_entry__.build();
                                            it travels to the GPU box with the snapshot, /root/reference does not)
-Reference sources are never committed: oracle/_ref/ is in .gitignore (and not in .gpurunignore).
+Reference sources are never committed: baseline/_ref/ (where the bench contract keeps the unmodified reference) is in
+.gitignore and not in .gpurunignore.
 
 Every reference module runs `while not src_dir.endswith("sfa")` at import
 (data_process/kitti_bev_utils.py:13-15, utils/evaluation_utils.py:11-13,
@@ -25,7 +26,7 @@ import os
 import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-INSTALLED_ROOT = os.path.join(_HERE, "_ref", "sfa")
+INSTALLED_ROOT = os.path.join(os.path.dirname(_HERE), "baseline", "_ref", "sfa")
 SOURCE_ROOT = "/root/reference"
 _COPIED = ("config", "data_process", "utils", "models", "losses")            # SURVEY.md §9's recipe
 _SCRIPTS = ("test6.py", "argoverse_test.py")                                 # functions are compiled out of these
@@ -50,7 +51,7 @@ def available() -> bool:
 
 
 def install(force=False) -> bool:
-    """Copy the reference's Python packages for this path into oracle/_ref/sfa (a directory whose name ends in
+    """Copy the reference's Python packages for this path into baseline/_ref/sfa (a directory whose name ends in
     "sfa", which is what the reference's import preamble looks for).  No-op when /root/reference is absent."""
     import shutil
     if not _has_reference(SOURCE_ROOT):

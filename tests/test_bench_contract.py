@@ -1,6 +1,6 @@
 """CPU: the parts of bench.py's contract that need no GPU — the algorithmic-byte formula of SURVEY.md §8d, the sharding of
 the 8192-frame stream (BASELINE configs[4]), and the reference arm's JSON line (the reference's own functions when the
-oracle/_ref copy or /root/reference is present, the oracle port otherwise)."""
+baseline/_ref copy or /root/reference is present, the oracle port otherwise)."""
 import json
 import os
 import subprocess

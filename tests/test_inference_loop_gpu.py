@@ -5,7 +5,7 @@
     eval) -> `_sigmoid` -> GPU decode K=50 (this repo) -> dense post-processing,
 
 driven the way test.py:120-173 drives it, everything staying on the device.  The reference model comes from the
-git-ignored copy oracle/_ref/sfa that `__graft_entry__.build()` makes (it travels to the GPU box with the snapshot).
+git-ignored copy baseline/_ref/sfa that `__graft_entry__.build()` makes (it travels to the GPU box with the snapshot).
 
 Checked: all 32 BEV maps fed to the backbone are bit-exact against the oracle; the detections decoded from the
 backbone's REAL head tensors (sigmoid outputs clamped at 1e-4 / 1-1e-4, i.e. with plateaus and ties, unlike synthetic
