@@ -588,7 +588,10 @@ def run_b200(args):
                     "traffic_algorithmic": traffic_alg, "traffic_source": traffic_src,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": int(KB[dominant] * frames_per_launch),
                     "frames_per_launch": int(frames_per_launch),
-                    "timing": "CUDA events around each launch of a serialised, un-captured pass of the same step"}
+                    "timing": "CUDA events around each launch of a serialised, un-captured pass of the same step",
+                    "note": "isolated launches of %d frames: alone, a launch this small pays its partial last wave and ramp in full "
+                            "(the same kernel at 32 frames per launch: 0.52); in the timed schedule a second engine fills those gaps "
+                            "— the in-schedule, whole-path figure is roofline_path" % int(frames_per_launch)}
     path_gbs = value / world * bytes_frame / 1e9
     roofline_path = {"bytes_per_frame": bytes_frame, "achieved": round(path_gbs, 1), "peak": hbm_gbs, "unit": "GB/s",
                      "frac": round(path_gbs / hbm_gbs, 4), "per": "GPU, whole path (all kernels of a step), from `value`"}
