@@ -823,7 +823,7 @@ def main():
     ap.add_argument("--config", default="headline", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--sets", type=int, default=4)
-    ap.add_argument("--pipelines", type=int, default=2,
+    ap.add_argument("--pipelines", type=int, default=3,
                     help="engines (own workspaces, outputs, streams) that take the steps in turn, so consecutive steps overlap")
     ap.add_argument("--lanes", type=int, default=1, help="independent BEV streams the batch is split over")
     ap.add_argument("--decode-stream", type=int, default=1, help="1: the decode runs on a stream of its own next to the BEV lane(s)")
