@@ -38,7 +38,14 @@ namespace {
 
 constexpr int kCandThreads = 512;
 constexpr int kCandWarps = kCandThreads / 32;
-constexpr int kCandRows = 16;              // rows of a slab
+#ifndef SFA_CAND_ROWS
+#define SFA_CAND_ROWS 19
+#endif
+// rows of a slab.  19: the 152-row KITTI head splits into exactly 8 slabs, 512 CTAs for a batch of 64 = one wave of the
+// 592 resident CTAs (16 rows: 10 slabs, 640 CTAs, a second wave of 48)
+constexpr int kCandRows = SFA_CAND_ROWS;
+constexpr int kQuadRows = (kCandRows + 3) / 4;   // slab rows per thread of the quad walker (4 row groups x kQuadRows >= kCandRows)
+static_assert(4 * kQuadRows <= 32 && kCandRows <= 32, "a thread's cells are the bits of one 32-bit mask");
 constexpr int kCapClasses = 8;             // plateau cap: classes a column group may span ...
 constexpr int kCapWords = 16;              // ... and 32-bit words per map row (w <= 512)
 #ifndef SFA_SEL_THREADS
@@ -182,15 +189,15 @@ peak_candidates_kernel(DecodeArgs a) {
     unsigned long long* list = a.cands + (size_t)b * frame_cap;
     const int ncols = C * w;
     // A thread's cells are the set bits of posmask / minmask.  Scalar walker: bit r = slab row r of column
-    // (c, x).  Quad walker: bit 4*i + j = slab row rg*4 + i of column (c, x + j).
+    // (c, x).  Quad walker: bit 4*i + j = slab row rg*kQuadRows + i of column (c, x + j).
     for (int col0 = 0; col0 < ncols; col0 += kCandThreads) {   // block-uniform trip count (barriers inside)
         int c = 0, x = 0, rg = 0;
         unsigned posmask = 0, minmask = 0;
         if (quad) {
             const int q = (col0 >> 2) + (tid & (kCandThreads / 4 - 1));   // quad of columns; kCandThreads / 4 quads per pass
-            rg = tid / (kCandThreads / 4);                                  // 4 slab rows each
+            rg = tid / (kCandThreads / 4);                                  // kQuadRows slab rows each
             const int w4 = w >> 2;
-            if (q < (ncols >> 2) && rg * 4 < rows) {
+            if (q < (ncols >> 2) && rg * kQuadRows < rows) {
                 c = q / w4;
                 x = (q - c * w4) * 4;
                 const uint32_t* tk = tkeys + (size_t)c * tplane + x;
@@ -203,13 +210,14 @@ peak_candidates_kernel(DecodeArgs a) {
                     return make_uint4(max(max(l, own.x), own.y), max(max(own.x, own.y), own.z),
                                       max(max(own.y, own.z), own.w), max(max(own.z, own.w), r));
                 };
-                uint4 h0 = hrow(rg * 4), h1 = hrow(rg * 4 + 1);
-                uint4 cur = own;   // keys of tile row rg*4 + 1 = slab row rg*4
+                uint4 h0 = hrow(rg * kQuadRows), h1 = hrow(rg * kQuadRows + 1);
+                uint4 cur = own;   // keys of tile row rg*kQuadRows + 1 = slab row rg*kQuadRows
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint4 h2 = hrow(rg * 4 + i + 2);
+                for (int i = 0; i < kQuadRows; ++i) {
+                    if (rg * kQuadRows + i >= kCandRows) break;   // (the last row group may be short: stay inside the tile)
+                    const uint4 h2 = hrow(rg * kQuadRows + i + 2);
                     const uint4 nxt = own;
-                    if (rg * 4 + i < rows) {
+                    if (rg * kQuadRows + i < rows) {
                         const uint32_t m0 = max(max(h0.x, h1.x), h2.x), m1 = max(max(h0.y, h1.y), h2.y);
                         const uint32_t m2 = max(max(h0.z, h1.z), h2.z), m3 = max(max(h0.w, h1.w), h2.w);
                         const unsigned p = (m0 == cur.x && cur.x > kZeroKey ? 1u : 0u) | (m1 == cur.y && cur.y > kZeroKey ? 2u : 0u) |
@@ -251,7 +259,7 @@ peak_candidates_kernel(DecodeArgs a) {
             }
         }
         auto cell_x = [&](int bit) -> int { return quad ? x + (bit & 3) : x; };
-        auto cell_r = [&](int bit) -> int { return quad ? rg * 4 + (bit >> 2) : bit; };
+        auto cell_r = [&](int bit) -> int { return quad ? rg * kQuadRows + (bit >> 2) : bit; };
         // ---- plateau cap ---------------------------------------------------------------------------
         // Among cells with EQUAL keys the top-K takes the lowest linear indices, so of the cells of this
         // column group that share one key only the K lowest-index ones can ever be selected.  Applied to
@@ -289,7 +297,7 @@ peak_candidates_kernel(DecodeArgs a) {
             }
             __syncthreads();
             if (warp == 0) {   // exclusive scan over the (<= 128) rows in (class, row) order = linear-index order
-                constexpr int per = kCapClasses * kCandRows / 32;
+                constexpr int per = (kCapClasses * kCandRows + 31) / 32;
                 unsigned v[per], run = 0;
 #pragma unroll
                 for (int q = 0; q < per; ++q) { v[q] = lane * per + q < n_rows ? caprow[lane * per + q] : 0u; run += v[q]; }
