@@ -743,7 +743,9 @@ int launch_decode(DecodeArgs a, void* workspace, size_t workspace_bytes, cudaStr
     a.cands = reinterpret_cast<unsigned long long*>(ws + kDecodeHeaderBytes + (((size_t)a.B * sizeof(uint32_t) + 255) / 256) * 256);
     a.vec4 = ((a.w & 3) == 0 && (reinterpret_cast<uintptr_t>(a.hm) & 15) == 0) ? 1 : 0;
 
-    if (tile_smem > 48 * 1024)
+    // the 48-KB default limit counts the kernel's static shared memory (plateau-cap bitmaps, ~11 KB) as well: opt in whenever
+    // the sum could pass it, not only when the tile alone does
+    if (tile_smem > 32 * 1024)
         SFA_CUDA_TRY(cudaFuncSetAttribute(peak_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
     dim3 cgrid((a.h + kCandRows - 1) / kCandRows, a.B);
     SFA_LAUNCH("peak_candidates", stream, peak_candidates_kernel<<<cgrid, kCandThreads, tile_smem, stream>>>(a));
