@@ -466,6 +466,10 @@ def run_b200(args):
         return run_loop32(args, torch, dev, fast, geom, dev_pts, B, N, sets, cpu_baseline, bytes_frame, lib)
 
     n_pipe = 1 if args.eager else max(1, args.pipelines)
+    # The library itself deals the 8-frame chunks of a call to two internal streams (sfa_bev_set_internal_lanes).  With several
+    # engines / lanes overlapping at this level that is redundant (measured: -4 %), so the multi-engine schedule turns it off;
+    # the `single_call` figure below is the library's default as one caller on one stream gets it.
+    lib.load().sfa_bev_set_internal_lanes(1 if (n_pipe > 1 or lanes > 1) else 0)
     engines = [Engine() for _ in range(n_pipe)]
     launches_per_step = 0
     cap_stream = torch.cuda.Stream(device=dev)
@@ -548,6 +552,42 @@ def run_b200(args):
     frames = B * args.steps * world
     value = frames / (ms_total * 1e-3)
 
+    # ---- the same step as ONE caller issues it: one engine, one BEV call per step on one stream (+ the decode stream),
+    #      the library's internal lanes at their default ------------------------------------------------------------
+    single_call = None
+    if not args.eager and args.only == "both" and (n_pipe > 1 or lanes > 1) and not args.no_single_call:
+        lib.load().sfa_bev_set_internal_lanes(0)
+        eng1 = Engine()
+        for s_ in range(min(sets, 4)):
+            eng1.step(s_)
+        torch.cuda.synchronize()
+        for s_ in range(sets):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=cap_stream):
+                eng1.step(s_)
+            eng1.graphs.append(g)
+        n1 = max(50, min(args.steps, 400))
+        for i in range(20):
+            eng1.graphs[i % sets].replay()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(n1):
+            eng1.graphs[i % sets].replay()
+        s1.record()
+        barrier()
+        ms1 = s0.elapsed_time(s1)
+        if world > 1:
+            t = torch.tensor([ms1], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms1 = float(t.item())
+        single_call = {"value": round(B * n1 * world / (ms1 * 1e-3), 1), "unit": "frames/s", "steps": n1,
+                       "ms_per_step": round(ms1 / n1, 5),
+                       "what": "one engine, steps back to back on one stream: one sfa_bev_rasterize call per step (the library overlaps "
+                               "its 8-frame chunks on 2 internal streams) + the decode on a second stream"}
+        lib.load().sfa_bev_set_internal_lanes(1)
+        del eng1
+
     # ---- per-kernel device time (un-captured, serialised pass, events around every library launch) ---------------
     torch.cuda.synchronize()
     with lib.profile() as prof:
@@ -617,7 +657,7 @@ def run_b200(args):
                                   (n_pipe, lanes, " + 1 decode stream" if (lanes > 1 or args.decode_stream) else ", decode on the same stream"),
                        "sharding": "frames, no collective on the data path"},
             "gpu_launches": int(launches_per_step * args.steps),
-            "e2e": e2e, "roofline": roofline, "roofline_path": roofline_path, "kernels_serialised": kern,
+            "e2e": e2e, "roofline": roofline, "roofline_path": roofline_path, "single_call": single_call, "kernels_serialised": kern,
             "cpu_baseline": cpu_baseline, "clocks": clocks.summary(t_begin, t_end),
         }
         if stream_info:
@@ -631,6 +671,7 @@ def run_b200(args):
 def run_e2e(args, torch, dist, dev, local_rank, world, fast, geom, host_set, B, N, engine, barrier):
     """The same metric through the reference-facing host-buffer C ABI: pinned host sweeps + heads in, host BEV maps +
     detections out, copies inside the timed region."""
+    pkg("_lib").load().sfa_bev_set_internal_lanes(0)   # the host pipeline as any caller gets it (library default)
     pts_h, heads_h = host_set
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     pts_pin = pin(pts_h.reshape(-1, 4))
@@ -835,6 +876,7 @@ def main():
     ap.add_argument("--separate-post", action="store_true", help="post_processing as its own launch instead of the decode's epilogue")
     ap.add_argument("--ragged-api", action="store_true", help="pass an offsets array instead of the uniform-batch form")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-single-call", action="store_true", help="skip the one-engine / one-stream secondary measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true",
                     help="profiling aid (ncu): plain launches instead of CUDA-graph replays, no settle window; "

@@ -54,6 +54,8 @@ PROTOTYPES = {
     "sfa_profile_end": (ctypes.c_int, [ctypes.POINTER(SfaKernelStat), i32]),
     "sfa_bev_workspace_bytes": (sz, [i32, i64, ctypes.POINTER(SfaBevParams)]),
     "sfa_bev_workspace_init": (ctypes.c_int, [c_void_p, sz, c_void_p]),
+    "sfa_bev_workspace_release": (ctypes.c_int, [c_void_p]),
+    "sfa_bev_set_internal_lanes": (ctypes.c_int, [i32]),
     "sfa_bev_band_plan": (ctypes.c_int, [ctypes.POINTER(SfaBevParams), ctypes.POINTER(i32), ctypes.POINTER(i32),
                                          ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(i32)]),
     "sfa_bev_rasterize": (ctypes.c_int, [c_void_p, c_void_p, i32, i64, ctypes.POINTER(SfaBevParams), c_void_p,

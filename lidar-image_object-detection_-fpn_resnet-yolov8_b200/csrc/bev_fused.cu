@@ -50,7 +50,7 @@ constexpr int kFusedSpecRecords = 4;                          // ... of which pr
 constexpr size_t kFusedStageBytes = (size_t)kFusedTile * sizeof(uint4);   // 16 KB
 // control block inside the workspace header: every counter alone in a 128-B line
 constexpr int kCtlLine = 32;                                   // uint32 per line
-constexpr size_t kFusedCtlOffset = 256;
+constexpr size_t kFusedCtlOffset = 2048;   // behind the two-kernel schedule's overflow-counter banks
 constexpr int kCtlTicket = 0;
 constexpr int kCtlTilesDone = 1;                               // + ring slot
 constexpr int kCtlBandsDone = 1 + kFusedMaxRing;

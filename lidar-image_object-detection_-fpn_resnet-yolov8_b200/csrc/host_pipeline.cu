@@ -165,6 +165,7 @@ static void pipeline_free(SfaPipeline* pl) {
     for (Lane& l : pl->lanes) {
         if (l.stream) cudaStreamSynchronize(l.stream);
         cudaFree(l.d_pts); cudaFree(l.d_offsets); cudaFreeHost(l.h_offsets); cudaFree(l.d_out);
+        if (l.d_ws) sfa_bev_workspace_release(l.d_ws);   // the rasteriser's side streams / events that belong to this workspace
         cudaFree(l.d_ws); cudaFree(l.d_heads); cudaFree(l.d_det); cudaFree(l.d_dec_ws);
         if (l.done) cudaEventDestroy(l.done);
         if (l.stream) cudaStreamDestroy(l.stream);

@@ -54,16 +54,26 @@ class BevRasterizer:
                                  "density table and a workspace at least as large")
             self.workspace, self._ws_ptr, self._ws_bytes = share_with.workspace, share_with._ws_ptr, share_with._ws_bytes
             self.lut, self.status = share_with.lut, share_with.status
+            self._owns_ws = False
             return
         with torch.cuda.device(self.device):
             self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
             off = (-self.workspace.data_ptr()) % 256
             self._ws_ptr = self.workspace.data_ptr() + off
             self._ws_bytes = nbytes
+            self._owns_ws = True
             self.lut = torch.from_numpy(geom.lut32.copy()).to(self.device)
             self.status = torch.zeros(2, dtype=torch.int32, device=self.device)
             _lib.check(self.lib.sfa_bev_workspace_init(ctypes.c_void_p(self._ws_ptr), self._ws_bytes,
                                                        _stream_ptr(self.device)))
+
+    def __del__(self):
+        # the library keeps two side streams + events per workspace (chunk-parallel lanes): hand them back with the workspace
+        try:
+            if getattr(self, "_owns_ws", False) and self.lib is not None:
+                self.lib.sfa_bev_workspace_release(ctypes.c_void_p(self._ws_ptr))
+        except Exception:
+            pass
 
     def __call__(self, points, offsets, max_points, out=None, mats=None, scales=None, hflip=None, second=None, out_second=None):
         """points [total,4] f32 cuda, offsets [B+1] i64 cuda (or None for a uniform batch of sweeps with
