@@ -542,3 +542,37 @@ def test_stream8192_shard_frames(cuda_device):
     assert host[..., 0].min() >= b["minX"] and host[..., 0].max() <= b["maxX"] and host[..., 2].min() >= b["minZ"] - 1e-6
     for i in range(len(ids)):
         _assert_bit_exact(got[i], O.make_bev_scatter(host[i], O.KITTI, True, np.float32), "stream frame %d" % ids[i])
+
+
+def test_bev_internal_lanes_give_identical_maps(cuda_device):
+    """sfa_bev_set_internal_lanes: the 8-frame chunks of one call on 1, 2 or 3 library-owned streams (fork / join around the
+    caller's stream) — identical maps, ragged batch with empty sweeps, several calls on one workspace, and inside a CUDA graph."""
+    fast, lib = pkg("fast"), pkg("_lib").load()
+    rng = np.random.default_rng(9)
+    lens = [int(rng.integers(0, 40000)) if i % 5 else 0 for i in range(37)]
+    sweeps = [O.synth_sweep(800 + i, n, O.KITTI, KINDS[i % len(KINDS)]) if n else np.zeros((0, 4), np.float32) for i, n in enumerate(lens)]
+    pts = torch.from_numpy(np.concatenate(sweeps)).to(cuda_device)
+    offsets = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int64, device=cuda_device)
+    want = [O.make_bev_scatter(s, O.KITTI, True, np.float32) for s in sweeps]
+    try:
+        for n_lanes in (1, 2, 3, 0):
+            assert lib.sfa_bev_set_internal_lanes(n_lanes) == 0
+            rast = fast.BevRasterizer(_geom(O.KITTI, algorithm=TWO_KERNEL), max_batch=len(lens), max_points=max(lens), device=cuda_device)
+            for attempt in range(2):
+                got = rast(pts, offsets, max(lens)).cpu().numpy()
+                for i in range(len(lens)):
+                    _assert_bit_exact(got[i], want[i], "lanes=%d frame %d" % (n_lanes, i))
+            out = torch.zeros((len(lens), 3, 608, 608), device=cuda_device)
+            g = torch.cuda.CUDAGraph()
+            s = torch.cuda.Stream(device=cuda_device)
+            s.wait_stream(torch.cuda.current_stream(cuda_device))
+            with torch.cuda.graph(g, stream=s):
+                rast(pts, offsets, max(lens), out=out)
+            out.zero_()
+            g.replay(); g.replay()
+            torch.cuda.synchronize()
+            assert np.array_equal(out.cpu().numpy().view(np.uint32), np.stack(want).view(np.uint32)), n_lanes
+            del g, rast
+        assert lib.sfa_bev_set_internal_lanes(9) != 0      # out of range: refused
+    finally:
+        lib.sfa_bev_set_internal_lanes(0)
