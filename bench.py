@@ -552,6 +552,58 @@ def run_b200(args):
     frames = B * args.steps * world
     value = frames / (ms_total * 1e-3)
 
+    # ---- stage ablation in the SAME schedule: the timed graphs again with one stage left out ---------------------------
+    stage = None
+    if not args.eager and args.only == "both" and not args.no_stage_ablation and rank == 0 and world == 1:
+        def timed_only(which, n):
+            saved = args.only
+            args.only = which
+            try:
+                graphs = []
+                for eng in engines:
+                    gs = []
+                    for s_ in range(sets):
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g, stream=cap_stream):
+                            eng.step(s_)
+                        gs.append(g)
+                    graphs.append(gs)
+            finally:
+                args.only = saved
+
+            def rep(i):
+                eng = engines[i % n_pipe]
+                if n_pipe == 1:
+                    graphs[0][i % sets].replay()
+                else:
+                    with torch.cuda.stream(eng.launch):
+                        graphs[i % n_pipe][i % sets].replay()
+            fork()
+            for i in range(3 * n_pipe):
+                rep(i)
+            join()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            fork()
+            for i in range(n):
+                rep(i)
+            join()
+            a1.record()
+            torch.cuda.synchronize()
+            return a0.elapsed_time(a1) / n
+        n_ab = max(60, min(args.steps, 400))
+        ms_bev, ms_dec = timed_only("bev", n_ab), timed_only("decode", n_ab)
+        hbm_gbs_, _ = peaks()
+        bev_gbs = bytes_bev * B / (ms_bev * 1e-3) / 1e9
+        stage = {"bev_only_ms_per_step": round(ms_bev, 5), "decode_only_ms_per_step": round(ms_dec, 5),
+                 "both_ms_per_step": round(ms_total / args.steps, 5),
+                 "decode_adds_ms_per_step": round(ms_total / args.steps - ms_bev, 5), "steps": n_ab,
+                 "bev_stage_roofline": {"achieved": round(bev_gbs, 1), "peak": hbm_gbs_, "unit": "GB/s", "frac": round(bev_gbs / hbm_gbs_, 4),
+                                        "bytes_per_frame": bytes_bev,
+                                        "what": "bev_bin + bev_band of a step as the timed schedule runs them (same engines, streams and "
+                                                "graphs, decode left out): algorithmic bytes / in-schedule time"}}
+
     # ---- the same step as ONE caller issues it: one engine, one BEV call per step on one stream (+ the decode stream),
     #      the library's internal lanes at their default ------------------------------------------------------------
     single_call = None
@@ -657,7 +709,8 @@ def run_b200(args):
                                   (n_pipe, lanes, " + 1 decode stream" if (lanes > 1 or args.decode_stream) else ", decode on the same stream"),
                        "sharding": "frames, no collective on the data path"},
             "gpu_launches": int(launches_per_step * args.steps),
-            "e2e": e2e, "roofline": roofline, "roofline_path": roofline_path, "single_call": single_call, "kernels_serialised": kern,
+            "e2e": e2e, "roofline": roofline, "roofline_path": roofline_path, "stage_ablation": stage, "single_call": single_call,
+            "kernels_serialised": kern,
             "cpu_baseline": cpu_baseline, "clocks": clocks.summary(t_begin, t_end),
         }
         if stream_info:
@@ -876,6 +929,7 @@ def main():
     ap.add_argument("--separate-post", action="store_true", help="post_processing as its own launch instead of the decode's epilogue")
     ap.add_argument("--ragged-api", action="store_true", help="pass an offsets array instead of the uniform-batch form")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-stage-ablation", action="store_true", help="skip the BEV-only / decode-only runs of the timed schedule")
     ap.add_argument("--no-single-call", action="store_true", help="skip the one-engine / one-stream secondary measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true",
