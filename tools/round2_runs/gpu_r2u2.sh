@@ -1,0 +1,14 @@
+#!/bin/bash
+# round 2: bev_band with the shared-memory reads of phases 2 / 3 issued per batch of slots
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_bev_gpu.py tests/test_augment_gpu.py -m gpu -x -q > gpurun_out/r2u2_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2u2_pytest.log
+B="python bench.py --no-e2e --no-cpu-baseline --steps 1500"
+ex() { python -c "import json,sys; l=json.loads(sys.stdin.read().strip().splitlines()[-1]); s=l.get('stage_ablation') or {}; k=l['kernels_serialised']; print('$1', round(l['value']), 'single', round((l.get('single_call') or {}).get('value',0)), 'bev_only_us', s.get('bev_only_ms_per_step'), 'band_ms', k['bev_band']['ms_per_step'])"; }
+for rep in 1 2 3; do $B 2>/dev/null | ex "batched"; done
+$B --config density1r 2>/dev/null | ex "batched density1r"
+$B --config argoverse 2>/dev/null | ex "batched argoverse"
+for ring in 8 32; do
+echo -n "single stream ring=$ring lanes1: "; SFA_BEV_TILED_RING=$ring SFA_BEV_INTERNAL_LANES=1 python tools/bev_run.py 200 3
+done
+SFA_DEBUG_TIMING=1 python -c "import __graft_entry__ as g; g.build()" 2>&1 | tail -1
+SFA_DEBUG_TIMING=1 SFA_BEV_TILED_RING=32 SFA_BEV_INTERNAL_LANES=1 python tools/band_timing.py | head -7
