@@ -684,6 +684,9 @@ def run_b200(args):
                     "note": "isolated launches of %d frames: alone, a launch this small pays its partial last wave and ramp in full "
                             "(the same kernel at 32 frames per launch: 0.52); in the timed schedule a second engine fills those gaps "
                             "— the in-schedule, whole-path figure is roofline_path" % int(frames_per_launch)}
+        if stage:   # the BEV stage (both kernels) in the timed schedule, decode left out: see stage_ablation
+            roofline["in_schedule_stage"] = {"kernels": "bev_bin + bev_band", "achieved": stage["bev_stage_roofline"]["achieved"],
+                                             "frac": stage["bev_stage_roofline"]["frac"]}
     path_gbs = value / world * bytes_frame / 1e9
     roofline_path = {"bytes_per_frame": bytes_frame, "achieved": round(path_gbs, 1), "peak": hbm_gbs, "unit": "GB/s",
                      "frac": round(path_gbs / hbm_gbs, 4), "per": "GPU, whole path (all kernels of a step), from `value`"}
