@@ -74,6 +74,31 @@ __device__ __forceinline__ void st_stream_f4(float4* p, const float4& v) {
                  : "memory");
 }
 
+// ---- shared-memory access through a 32-bit shared::cta address ----------------------------------
+// For sm_100a nvcc rebuilds the shared window base (S2UR SR_CgaCtaId + three uniform ops) at every access to a __shared__
+// array; in an issue-bound kernel those are a tenth of the instructions.  The hot sites take ONE base register
+// (smem_addr_u32 of the kernel's shared struct) plus compile-time offsets instead.
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    return v;
+}
+// if (pred) st.shared.v4
+__device__ __forceinline__ void sts_v4_if(bool pred, uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %5, 0; @p st.shared.v4.u32 [%0], {%1,%2,%3,%4}; }" ::"r"(saddr), "r"(a), "r"(b),
+                 "r"(c), "r"(d), "r"((uint32_t)pred)
+                 : "memory");
+}
+// pred ? atomicAdd(shared u32, 1) : `otherwise`
+__device__ __forceinline__ uint32_t atoms_inc_if(bool pred, uint32_t saddr, uint32_t otherwise) {
+    uint32_t old;
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; mov.u32 %0, %3; @p atom.shared.add.u32 %0, [%1], 1; }"
+                 : "=r"(old)
+                 : "r"(saddr), "r"((uint32_t)pred), "r"(otherwise)
+                 : "memory");
+    return old;
+}
+
 // ---- TMA bulk copies (cp.async.bulk, 1-D, no tensor map) ----------------------------------------
 __device__ __forceinline__ uint32_t smem_addr_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
