@@ -576,3 +576,31 @@ def test_bev_internal_lanes_give_identical_maps(cuda_device):
         assert lib.sfa_bev_set_internal_lanes(9) != 0      # out of range: refused
     finally:
         lib.sfa_bev_set_internal_lanes(0)
+
+
+@pytest.mark.parametrize("algorithm", ALGOS)
+@pytest.mark.parametrize("min_z", [-2.73, 0.0, -1e-30])
+def test_bev_heights_at_and_just_above_min_z(cuda_device, algorithm, min_z):
+    """bev_band may max-reduce the bits of the FINAL height z / max_height instead of an ordered key of z (filter on, power-of-two
+    max_height, |minZ| not tiny: `hkey` in tiled_launch_chunk).  Heights of exactly 0 (z == minZ: the key of an occupied cell then
+    equals the empty cell's), of one and a few ulps above minZ, alone in a cell and sharing one (ties on 0 included); with
+    minZ = 0 or tiny the sweep holds denormal z values and the kernel has to take the ordered-key form."""
+    g = O.Geometry(boundary={"minX": 0, "maxX": 50, "minY": -25, "maxY": 25, "minZ": min_z, "maxZ": min_z + 4.0})
+    rng = np.random.default_rng(5)
+    n = 40000
+    s = O.synth_sweep(123, n, g, "uniform")
+    mz = np.float32(min_z)
+    steps = [mz]
+    for _ in range(4):
+        steps.append(np.nextafter(steps[-1], np.float32(np.inf), dtype=np.float32))
+    if min_z == 0.0 or abs(min_z) < 1e-20:
+        steps += [np.float32(1e-45), np.float32(3e-45), np.float32(1e-39), np.float32(2e-38), mz + np.float32(1e-38)]
+    zs = np.array(steps, np.float32)
+    s[: n // 2, 2] = zs[rng.integers(0, len(zs), n // 2)]
+    # a quarter of those share cells: many points on few positions
+    k = n // 8
+    s[:k, 0] = np.float32(10.0) + (rng.integers(0, 40, k) * g.DISCRETIZATION).astype(np.float32)
+    s[:k, 1] = np.float32(1.0)
+    got, _ = _run_batch(cuda_device, [s, s[::-1].copy()], g, algorithm=algorithm)
+    _assert_bit_exact(got[0], O.make_bev_scatter(s, g, True, np.float32), "min_z=%g" % min_z)
+    _assert_bit_exact(got[1], O.make_bev_scatter(s[::-1].copy(), g, True, np.float32), "min_z=%g reversed" % min_z)
