@@ -99,6 +99,27 @@ __device__ __forceinline__ uint32_t atoms_inc_if(bool pred, uint32_t saddr, uint
     return old;
 }
 
+// the same with a compile-time byte offset folded into the address ([reg + imm])
+template <int OFF> __device__ __forceinline__ uint32_t lds_at(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1 + %2];" : "=r"(v) : "r"(saddr), "n"(OFF) : "memory");
+    return v;
+}
+template <int OFF> __device__ __forceinline__ void sts_at(uint32_t saddr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0 + %1], %2;" ::"r"(saddr), "n"(OFF), "r"(v) : "memory");
+}
+template <int OFF> __device__ __forceinline__ void red_max_at(uint32_t saddr, uint32_t v) {
+    asm volatile("red.shared.max.u32 [%0 + %1], %2;" ::"r"(saddr), "n"(OFF), "r"(v) : "memory");
+}
+template <int OFF> __device__ __forceinline__ void red_inc_at(uint32_t saddr) {
+    asm volatile("red.shared.add.u32 [%0 + %1], 1;" ::"r"(saddr), "n"(OFF) : "memory");
+}
+template <int OFF> __device__ __forceinline__ uint32_t cas_at(uint32_t saddr, uint32_t expect, uint32_t desired) {
+    uint32_t old;
+    asm volatile("atom.shared.cas.b32 %0, [%1 + %2], %3, %4;" : "=r"(old) : "r"(saddr), "n"(OFF), "r"(expect), "r"(desired) : "memory");
+    return old;
+}
+
 // ---- TMA bulk copies (cp.async.bulk, 1-D, no tensor map) ----------------------------------------
 __device__ __forceinline__ uint32_t smem_addr_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
