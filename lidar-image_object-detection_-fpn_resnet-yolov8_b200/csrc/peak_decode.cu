@@ -103,7 +103,10 @@ __device__ __forceinline__ uint32_t kept_key(uint32_t own, uint32_t m, bool do_n
     return (own == kPosInfKey || own == kNegInfKey) ? kNanKey : kZeroKey;
 }
 
-__global__ void __launch_bounds__(kCandThreads, 4)
+#ifndef SFA_CAND_MIN_CTAS
+#define SFA_CAND_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(kCandThreads, SFA_CAND_MIN_CTAS)
 peak_candidates_kernel(DecodeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned int warp_sums[kCandWarps];
@@ -119,7 +122,13 @@ peak_candidates_kernel(DecodeArgs a) {
     constexpr int trows = kCandRows + 2;
     const int tplane = trows * w;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { grp_min = 0xFFFFFFFFu; grp_max = 0; grp_nmin = 0; }
+    __shared__ __align__(8) unsigned long long load_bar;   // vec4 staging: the slab's TMA bulk loads complete on it
+    __shared__ unsigned int grp_raw;                        // ... and the largest raw bit pattern loaded
+    if (tid == 0) {
+        grp_min = 0xFFFFFFFFu; grp_max = 0; grp_nmin = 0; grp_raw = 0;
+        if (a.vec4) mbar_init(&load_bar, 1);
+    }
+    fence_proxy_async_smem();   // (the mbarrier's init, before a bulk copy signals it)
     __syncthreads();   // before any warp's atomicMin on grp_min
 
     // ---- stage slab + halo rows (r0-1 .. r0+rows) as orderable keys ---------------------------------
@@ -134,7 +143,53 @@ peak_candidates_kernel(DecodeArgs a) {
         const int y_lo = r0 - 1;
         const int tr_first = y_lo < 0 ? 1 : 0;          // first tile row inside the map
         const int tr_end = min(rows + 2, h - y_lo);     // one past the last tile row inside the map
+        bool staged = false;
         if (a.vec4) {
+            // Fast staging.  The in-map rows of a class are ONE contiguous run of the plane: thread 0 fetches the C runs with
+            // TMA bulk loads straight into the tile (no registers, no per-thread address arithmetic, one latency for the whole
+            // slab), then every thread turns its share of the floats into keys IN PLACE.  For positive finite values —
+            // any sigmoid output — the key is just bits | 0x80000000; a tile holding anything else (sign bit, inf, NaN: the
+            // largest RAW bit pattern is then >= 0x7F800000) is staged again by the general loop below.
+            const int n_in = (tr_end - tr_first) * w;   // words per class
+            if (tid == 0) {
+                mbar_expect_tx(&load_bar, (uint32_t)(C * n_in) * 4u);
+                for (int c = 0; c < C; ++c)
+                    bulk_load_g2s(tkeys + (size_t)c * tplane + tr_first * w, hmb + (size_t)c * hw + (ptrdiff_t)(y_lo + tr_first) * w,
+                                  (uint32_t)n_in * 4u, &load_bar);
+            }
+            for (int c = 0; c < C; ++c) {   // rows outside the map (first / last slab only): key 0
+                uint32_t* tc = tkeys + (size_t)c * tplane;
+                for (int i = tid; i < tr_first * w; i += kCandThreads) tc[i] = 0u;
+                for (int i = tr_end * w + tid; i < tplane; i += kCandThreads) tc[i] = 0u;
+            }
+            mbar_wait(&load_bar, 0);
+            const bool sg = a.apply_sigmoid != 0;
+            uint32_t raw_max = 0, raw_min = 0xFFFFFFFFu;
+            const int n4 = n_in >> 2;
+            for (int c = 0; c < C; ++c) {
+                uint4* d = reinterpret_cast<uint4*>(tkeys + (size_t)c * tplane + tr_first * w);
+                for (int i = tid; i < n4; i += kCandThreads) {
+                    uint4 bts = d[i];
+                    if (sg) {
+                        bts.x = __float_as_uint(sigmoid_clamped(__uint_as_float(bts.x))); bts.y = __float_as_uint(sigmoid_clamped(__uint_as_float(bts.y)));
+                        bts.z = __float_as_uint(sigmoid_clamped(__uint_as_float(bts.z))); bts.w = __float_as_uint(sigmoid_clamped(__uint_as_float(bts.w)));
+                    }
+                    raw_max = max(raw_max, max(max(bts.x, bts.y), max(bts.z, bts.w)));
+                    raw_min = min(raw_min, min(min(bts.x, bts.y), min(bts.z, bts.w)));
+                    d[i] = make_uint4(bts.x | 0x80000000u, bts.y | 0x80000000u, bts.z | 0x80000000u, bts.w | 0x80000000u);
+                }
+            }
+            raw_max = __reduce_max_sync(0xFFFFFFFFu, raw_max);
+            if (lane == 0) atomicMax(&grp_raw, raw_max);
+            __syncthreads();
+            staged = grp_raw < 0x7F800000u;   // block-uniform
+            if (staged) {
+                tile_min = raw_min == 0xFFFFFFFFu ? raw_min : (raw_min | 0x80000000u);
+                tile_max = raw_max | 0x80000000u;
+            }
+        }
+        if (staged) {
+        } else if (a.vec4) {
             const int w4 = w >> 2, tplane4 = trows * w4;
             const int lo4 = tr_first * w4, hi4 = tr_end * w4;
             const int hw4 = hw >> 2;
