@@ -120,6 +120,13 @@ template <int OFF> __device__ __forceinline__ uint32_t cas_at(uint32_t saddr, ui
     return old;
 }
 
+// ---- programmatic dependent launch (griddepcontrol) ----------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become resident once every CTA of the kernel
+// in front of it has called grid_launch_dependents() (or exited); it must call grid_dependency_wait() before it touches anything
+// that kernel wrote.  Both are no-ops in an ordinary launch.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- TMA bulk copies (cp.async.bulk, 1-D, no tensor map) ----------------------------------------
 __device__ __forceinline__ uint32_t smem_addr_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
