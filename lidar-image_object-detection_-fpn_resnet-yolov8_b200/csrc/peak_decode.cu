@@ -189,6 +189,7 @@ peak_candidates_kernel(DecodeArgs a) {
             }
         }
         if (staged) {
+            // done above
         } else if (a.vec4) {
             const int w4 = w >> 2, tplane4 = trows * w4;
             const int lo4 = tr_first * w4, hi4 = tr_end * w4;
